@@ -1,0 +1,111 @@
+"""ctypes binding of libdta_b200.so — the ONLY route from Python to the kernels.
+
+Signatures mirror ``include/dta_b200.h`` one to one.  There is deliberately no
+fallback: if the shared library is missing or fails to load, every device-side
+op raises.  PyTorch is used for memory and streams only; the library sees raw
+device pointers and a ``cudaStream_t``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libdta_b200.so"
+_lib: Optional[C.CDLL] = None
+
+ABI_VERSION = 1
+TILE = 128
+
+
+class DtaError(RuntimeError):
+    pass
+
+
+class AttnShape(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int32), ("n_pad", C.c_int32),
+        ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32),
+        ("q_row_stride", C.c_int64), ("q_head_stride", C.c_int64),
+        ("k_row_stride", C.c_int64), ("k_head_stride", C.c_int64),
+        ("v_row_stride", C.c_int64), ("v_head_stride", C.c_int64),
+        ("o_row_stride", C.c_int64), ("o_head_stride", C.c_int64),
+        ("scale", C.c_float),
+    ]
+
+
+class AttnMeta(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("subtree_end", "kmax_end", "kmin_end", "q_order", "k_order", "k_qlast")]
+
+
+_P, _I, _L, _F, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol declared in include/dta_b200.h
+SIGNATURES = {
+    "dta_last_error": (C.c_char_p, []),
+    "dta_abi_version": (_I, []),
+    "dta_lcp_adjacent": (_I, [_P, _P, _I, _P, _P, _P]),
+    "dta_trie_workspace_bytes": (_Z, [_I]),
+    "dta_trie_linearize": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "dta_trie_paths": (_I, [_P, _P, _P, _I, _P, _L, _P, _P, _P]),
+    "dta_tile_meta": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dta_tree_attn_fwd": (_I, [_P, _P, _P, _P, _P, C.POINTER(AttnMeta), C.POINTER(AttnShape), _P]),
+    "dta_tree_attn_bwd_workspace_bytes": (_Z, [C.POINTER(AttnShape)]),
+    "dta_tree_attn_bwd": (_I, [_P] * 9 + [C.POINTER(AttnMeta), C.POINTER(AttnShape), _P, _P]),
+    "dta_logprob_row_stats": (_I, [_P, _I, _L, _L, _L, _F, _P, _P]),
+    "dta_logprob_gather_labels": (_I, [_P, _I, _L, _L, _F, _P, _P, _L, _L, _P, _L, _P]),
+    "dta_logprob_finalize": (_I, [_P, _I, _L, _P, _P, _P, _P]),
+    "dta_logprob_bwd": (_I, [_P, _I, _L, _L, _L, _F, _P, _P, _P, _P, _P, _L, _P]),
+    "dta_logprob_bwd_scatter": (_I, [_P, _I, _L, _L, _F, _P, _P, _P, _L, _L, _P]),
+    "dta_logprob_rowsum_grad": (_I, [_P, _P, _L, _P, _P]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load (building first if allowed and needed) the C-ABI library; raise if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        if not build_if_missing or os.environ.get("DTA_NO_BUILD") == "1":
+            raise DtaError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        from ._build import build_library
+        build_library()
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dta_abi_version() != ABI_VERSION:
+        raise DtaError(f"ABI mismatch: library {lib.dta_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise DtaError(f"libdta_b200 error {rc}: {load().dta_last_error().decode(errors='replace')}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise DtaError("dynamictreeattn_b200 device ops need CUDA tensors (there is no CPU fallback)")

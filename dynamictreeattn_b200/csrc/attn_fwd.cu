@@ -1,0 +1,393 @@
+// attn_fwd.cu — tree-masked flash attention forward for sm_100a (tcgen05 + TMEM + TMA).
+//
+// One pass over the DFS-linearised trie replaces the reference's per-push HF attention
+// calls against the KV stack (tree_training_engine.py:182-186, 248-252).  Key k is visible
+// to query q iff k <= q < subtree_end[k].
+//
+// Work decomposition
+//   CTA          = one 128-query tile x one pair of query heads that share a KV head (GQA),
+//                  so both 128x128 score tiles consume the SAME K/V tiles and the SAME mask.
+//   key tiles    = only tiles with at least one visible pair are visited ("live" tiles:
+//                  kmax_end[tile] > q0); a live tile is FULL (no masking at all) when it lies
+//                  strictly below the diagonal and kmin_end[tile] >= q1, otherwise the
+//                  ancestor test is applied per element.
+//   warp roles   = warp 0: TMA producer      warp 1: tcgen05.mma issuer + TMEM owner
+//                  warps 4-7 : softmax / epilogue for tile A (TMEM lanes = query rows)
+//                  warps 8-11: softmax / epilogue for tile B
+//   TMEM (512 c) = S_A[0,128) S_B[128,256) O_A[256,384) O_B[384,512); P (bf16) overwrites
+//                  the first 64 columns of its own S tile and feeds the PV MMA from TMEM.
+//   pipeline     = QK_A(0) QK_B(0) | PV_A(i) QK_A(i+1) | PV_B(i) QK_B(i+1) | ...  so the
+//                  softmax of one tile overlaps the tensor work of the other.
+//   softmax      = online, base-2, lazy rescale (O is rescaled only when the row max grows
+//                  by more than 2^8), one thread per query row -> no shuffles.
+#include "dta_common.cuh"
+#include "dta_ptx.cuh"
+#include "../../include/dta_b200.h"
+
+namespace dta {
+
+static constexpr int kBM = 128;       // queries per tile
+static constexpr int kBN = 128;       // keys per tile
+static constexpr int kD = 128;        // head dim
+static constexpr int kHalfBytes = kBM * 128;          // one [128 rows][64 bf16] swizzled half-tile
+static constexpr int kTileBytes = 2 * kHalfBytes;     // 32 KB
+static constexpr int kStages = 2;
+static constexpr int kFwdThreads = 384;
+static constexpr int kMaxLive = 4096;
+static constexpr float kLog2e = 1.4426950408889634f;
+static constexpr float kLn2 = 0.6931471805599453f;
+static constexpr float kRescaleThreshold = 8.0f;      // log2 units
+
+struct FwdSmem {
+  // offsets inside the 1024-aligned dynamic shared buffer
+  static constexpr int q = 0;                                  // 2 tiles
+  static constexpr int k = q + 2 * kTileBytes;                 // kStages tiles
+  static constexpr int v = k + kStages * kTileBytes;           // kStages tiles
+  static constexpr int live = v + kStages * kTileBytes;        // int32[kMaxLive]
+  static constexpr int bars = live + kMaxLive * 4;             // mbarriers
+  static constexpr int n_bars = 1 + 4 * kStages + 6;
+  static constexpr int misc = bars + n_bars * 8;               // tmem addr, n_live
+  static constexpr int total = misc + 16;
+};
+
+struct FwdParams {
+  __nv_bfloat16* out;
+  float* lse;
+  const int32_t* subtree_end;
+  const int32_t* kmax_end;
+  const int32_t* kmin_end;
+  const int32_t* q_order;
+  int n_nodes, n_pad, n_tiles;
+  int n_q_heads, n_kv_heads, group, pairs_per_kv;
+  int64_t o_row_stride, o_head_stride;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + FwdSmem::q;
+  uint8_t* sK = smem + FwdSmem::k;
+  uint8_t* sV = smem + FwdSmem::v;
+  int32_t* sLive = reinterpret_cast<int32_t*>(smem + FwdSmem::live);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::bars);
+  uint64_t* bar_q_full = bars;
+  uint64_t* bar_k_full = bars + 1;
+  uint64_t* bar_k_empty = bar_k_full + kStages;
+  uint64_t* bar_v_full = bar_k_empty + kStages;
+  uint64_t* bar_v_empty = bar_v_full + kStages;
+  uint64_t* bar_s_full = bar_v_empty + kStages;   // [2] per tile
+  uint64_t* bar_p_full = bar_s_full + 2;          // [2]
+  uint64_t* bar_o_final = bar_p_full + 2;         // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + FwdSmem::misc);
+  int* s_nlive = reinterpret_cast<int*>(smem + FwdSmem::misc + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- which work item -----------------------------------------------------------------
+  const int n_pairs = p.n_kv_heads * p.pairs_per_kv;
+  const int qtile = p.q_order[blockIdx.x / n_pairs];
+  const int pair = blockIdx.x % n_pairs;
+  const int kvh = pair / p.pairs_per_kv;
+  const int head_a = kvh * p.group + 2 * (pair % p.pairs_per_kv);
+  const bool valid_b = (2 * (pair % p.pairs_per_kv) + 1) < p.group;
+  const int q0 = qtile * kBM, q1 = q0 + kBM;
+
+  // ---- setup ---------------------------------------------------------------------------
+  if (warp == 0) {
+    // ordered compaction of the live key tiles of this query tile
+    int count = 0;
+    for (int base = 0; base <= qtile; base += 32) {
+      const int j = base + lane;
+      bool is_live = false, partial = true;
+      if (j <= qtile) {
+        is_live = p.kmax_end[j] > q0;
+        partial = !(j < qtile && p.kmin_end[j] >= q1);
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, is_live);
+      if (is_live) {
+        const int pos = count + __popc(ballot & ((1u << lane) - 1u));
+        if (pos < kMaxLive) sLive[pos] = (j << 1) | (partial ? 1 : 0);
+      }
+      count += __popc(ballot);
+    }
+    if (lane == 0) {
+      *s_nlive = count;
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_k);
+      tma_prefetch_desc(&tmap_v);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(bar_q_full, 1);
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(bar_k_full + s, 1);
+        mbar_init(bar_k_empty + s, 1);
+        mbar_init(bar_v_full + s, 1);
+        mbar_init(bar_v_empty + s, 1);
+      }
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(bar_s_full + t, 1);
+        mbar_init(bar_p_full + t, 128);
+        mbar_init(bar_o_final + t, 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(s_tmem, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const int n_live = *s_nlive;
+
+  // Register re-split (per role branch so ptxas sees it): warps 0-3 release, softmax warps take.
+  if (warp == 0) {
+    // ================================ TMA producer =======================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q_full, (valid_b ? 2u : 1u) * kTileBytes);
+      for (int t = 0; t < (valid_b ? 2 : 1); ++t)
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(sQ + t * kTileBytes + h * kHalfBytes, &tmap_q, bar_q_full, h * 64, head_a + t, q0);
+      for (int it = 0; it < n_live; ++it) {
+        const int j = sLive[it] >> 1;
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(bar_k_empty + st, ph ^ 1);
+        mbar_arrive_expect_tx(bar_k_full + st, kTileBytes);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(sK + st * kTileBytes + h * kHalfBytes, &tmap_k, bar_k_full + st, h * 64, kvh, j * kBN);
+        mbar_wait(bar_v_empty + st, ph ^ 1);
+        mbar_arrive_expect_tx(bar_v_full + st, kTileBytes);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(sV + st * kTileBytes + h * kHalfBytes, &tmap_v, bar_v_full + st, h * 64, kvh, j * kBN);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kBM, kBN, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kBM, kD, false, true);
+      const int n_t = valid_b ? 2 : 1;
+      auto issue_qk = [&](int t, int st) {
+        const uint32_t a0 = smem_u32(sQ + t * kTileBytes), b0 = smem_u32(sK + st * kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < kD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+          umma_ss(tmem + t * 128, make_sdesc_sw128(a0 + off, 16, 1024), make_sdesc_sw128(b0 + off, 16, 1024),
+                  idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_s_full + t);
+      };
+      auto issue_pv = [&](int t, int st, bool first) {
+        const uint32_t b0 = smem_u32(sV + st * kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < kBN / 16; ++kk) {
+          umma_ts(tmem + 256 + t * 128, tmem + t * 128 + kk * 8, make_sdesc_sw128(b0 + kk * 2048, kHalfBytes, 1024),
+                  idesc_pv, (first && kk == 0) ? 0u : 1u);
+        }
+      };
+      mbar_wait(bar_q_full, 0);
+      mbar_wait(bar_k_full + 0, 0);
+      tc_fence_after();
+      for (int t = 0; t < n_t; ++t) issue_qk(t, 0);
+      umma_commit(bar_k_empty + 0);
+      for (int it = 0; it < n_live; ++it) {
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        const bool has_next = it + 1 < n_live;
+        const int nst = (it + 1) % kStages;
+        const uint32_t nph = ((it + 1) / kStages) & 1;
+        mbar_wait(bar_v_full + st, ph);
+        if (has_next) mbar_wait(bar_k_full + nst, nph);
+        for (int t = 0; t < n_t; ++t) {
+          mbar_wait(bar_p_full + t, it & 1);
+          tc_fence_after();
+          issue_pv(t, st, it == 0);
+          if (has_next) issue_qk(t, nst);
+        }
+        umma_commit(bar_v_empty + st);
+        if (has_next) umma_commit(bar_k_empty + nst);
+      }
+      for (int t = 0; t < n_t; ++t) umma_commit(bar_o_final + t);
+    }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  } else {
+    // ================================ softmax + epilogue =================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int t = (warp - 4) >> 2;                 // tile A / B
+    if (t == 0 || valid_b) {
+      const int row = ((warp & 3) << 5) | lane;    // TMEM lane == query row inside the tile
+      const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) << 5) << 16;
+      const uint32_t tS = tmem + lane_addr + t * 128;
+      const uint32_t tO = tmem + lane_addr + 256 + t * 128;
+      const int q = q0 + row;
+      const int head = head_a + t;
+      float m2 = -INFINITY;   // running max, log2 domain (already multiplied by scale_log2)
+      float l = 0.f;          // running sum of 2^(z - m2)
+
+      for (int it = 0; it < n_live; ++it) {
+        const int entry = sLive[it];
+        const int k0 = (entry >> 1) * kBN;
+        mbar_wait(bar_s_full + t, it & 1);
+        tc_fence_after();
+        float s[kBN];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, reinterpret_cast<uint32_t*>(s) + c * 32);
+        tmem_ld_wait();
+
+        if (entry & 1) {  // boundary tile: per-element ancestor test
+          const int4* ends = reinterpret_cast<const int4*>(p.subtree_end + k0);
+#pragma unroll
+          for (int c4 = 0; c4 < kBN / 4; ++c4) {
+            const int4 e = __ldg(ends + c4);
+            const int kb = k0 + c4 * 4;
+            if (!(kb + 0 <= q && q < e.x)) s[c4 * 4 + 0] = -INFINITY;
+            if (!(kb + 1 <= q && q < e.y)) s[c4 * 4 + 1] = -INFINITY;
+            if (!(kb + 2 <= q && q < e.z)) s[c4 * 4 + 2] = -INFINITY;
+            if (!(kb + 3 <= q && q < e.w)) s[c4 * 4 + 3] = -INFINITY;
+          }
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int c = 1; c < kBN; ++c) mx = fmaxf(mx, s[c]);
+        mx *= p.scale_log2;
+
+        // lazy rescale: keep the stale max unless the new one is > 2^8 larger
+        float alpha = 1.f;
+        if (mx > m2 + kRescaleThreshold) {
+          alpha = fast_exp2(m2 - mx);  // m2 == -inf -> 0
+          m2 = mx;
+        }
+        if (it > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+          // O_t is stable: s_full(it) was committed after PV_t(it-1)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tO + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+        l *= alpha;
+        const float mref = (m2 == -INFINITY) ? 0.f : m2;
+        float lsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fast_exp2(fmaf(s[c * 32 + i], p.scale_log2, -mref));
+            const float p1 = fast_exp2(fmaf(s[c * 32 + i + 1], p.scale_log2, -mref));
+            lsum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_x16(tS + c * 16, pk);
+        }
+        l += lsum;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_p_full + t);
+      }
+
+      // ---- epilogue: O / l -> bf16, LSE -----------------------------------------------
+      mbar_wait(bar_o_final + t, 0);
+      tc_fence_after();
+      const float inv_l = l > 0.f ? 1.f / l : 0.f;
+      if (q < p.n_pad) {
+        float lse = 0.f;
+        if (q < p.n_nodes) lse = (m2 + log2f(l)) * kLn2;
+        p.lse[static_cast<int64_t>(head) * p.n_pad + q] = lse;
+      }
+      __nv_bfloat16* orow = p.out + static_cast<int64_t>(q) * p.o_row_stride + static_cast<int64_t>(head) * p.o_head_stride;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld_x32(tO + c * 32, o);
+        tmem_ld_wait();
+        if (q < p.n_nodes) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + i) = w;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown --------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace dta
+
+using namespace dta;
+
+extern "C" int dta_tree_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
+                                 const dta_attn_meta_t* meta, const dta_attn_shape_t* sh, dta_stream_t stream) {
+  DTA_REQUIRE(q && k && v && out && lse && meta && sh, "NULL pointer argument");
+  DTA_REQUIRE(sh->head_dim == kD, "head_dim must be %d (got %d)", kD, sh->head_dim);
+  DTA_REQUIRE(sh->n_nodes >= 1 && sh->n_pad % DTA_TILE == 0 && sh->n_pad >= sh->n_nodes &&
+                  sh->n_pad - sh->n_nodes < DTA_TILE,
+              "n_pad must be n_nodes rounded up to %d", DTA_TILE);
+  DTA_REQUIRE(sh->n_kv_heads >= 1 && sh->n_q_heads % sh->n_kv_heads == 0, "n_q_heads must be a multiple of n_kv_heads");
+  DTA_REQUIRE(sh->n_pad / DTA_TILE <= kMaxLive, "trie too large: %d tiles > %d", sh->n_pad / DTA_TILE, kMaxLive);
+  DTA_REQUIRE(meta->subtree_end && meta->kmax_end && meta->kmin_end && meta->q_order, "NULL metadata pointer");
+  DTA_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (sh->o_row_stride % 8) == 0 && (sh->o_head_stride % 8) == 0,
+              "out must be 16-byte aligned with strides that are multiples of 8 elements");
+  DTA_REQUIRE((reinterpret_cast<uintptr_t>(meta->subtree_end) & 15) == 0, "subtree_end must be 16-byte aligned");
+
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bf16_rows(&tq, q, sh->n_nodes, sh->n_q_heads, kD, sh->q_row_stride, sh->q_head_stride, kBM))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tk, k, sh->n_nodes, sh->n_kv_heads, kD, sh->k_row_stride, sh->k_head_stride, kBN))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tv, v, sh->n_nodes, sh->n_kv_heads, kD, sh->v_row_stride, sh->v_head_stride, kBN))) return rc;
+
+  FwdParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.subtree_end = meta->subtree_end;
+  p.kmax_end = meta->kmax_end;
+  p.kmin_end = meta->kmin_end;
+  p.q_order = meta->q_order;
+  p.n_nodes = sh->n_nodes;
+  p.n_pad = sh->n_pad;
+  p.n_tiles = sh->n_pad / DTA_TILE;
+  p.n_q_heads = sh->n_q_heads;
+  p.n_kv_heads = sh->n_kv_heads;
+  p.group = sh->n_q_heads / sh->n_kv_heads;
+  p.pairs_per_kv = (p.group + 1) / 2;
+  p.o_row_stride = sh->o_row_stride;
+  p.o_head_stride = sh->o_head_stride;
+  p.scale_log2 = sh->scale * kLog2e;
+
+  const int smem_bytes = FwdSmem::total + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DTA_CHECK_CUDA(cudaFuncSetAttribute(tree_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  const int grid = p.n_tiles * p.n_kv_heads * p.pairs_per_kv;
+  tree_attn_fwd_kernel<<<grid, kFwdThreads, smem_bytes, stream>>>(tq, tk, tv, p);
+  DTA_CHECK_CUDA(cudaGetLastError());
+  return DTA_OK;
+}

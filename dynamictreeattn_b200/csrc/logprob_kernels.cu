@@ -1,0 +1,364 @@
+// logprob_kernels.cu — fused per-token log-prob / entropy over a vocab shard, fwd + bwd.
+//
+// Replaces the fp32 log_softmax + gather + entropy of the reference
+// (vocab_parallel.py:13-27) and its vocab-parallel autograd functions
+// (vocab_parallel.py:117-166, 249-321, 324-370).  HBM-bound: the forward reads each logit
+// once (online softmax, 16-byte loads), the backward reads it once and writes the gradient
+// once, optionally in place.  Per row the forward emits 16 bytes {m, sum e^(x-m),
+// sum x e^(x-m), 0}; that is all a vocab-parallel rank has to exchange.
+#include "dta_common.cuh"
+#include "../../include/dta_b200.h"
+#include <cuda_bf16.h>
+
+namespace dta {
+
+static constexpr float kLog2e = 1.4426950408889634f;
+static constexpr float kLn2 = 0.6931471805599453f;
+static constexpr int kRowThreads = 512;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct RowStat {  // running (max, sum e^(x-m), sum raw*e^(x-m)); x = raw * inv_temp
+  float m, s, t;
+};
+__device__ __forceinline__ RowStat merge(RowStat a, RowStat b) {
+  const float m = fmaxf(a.m, b.m);
+  if (m == -INFINITY) return RowStat{m, 0.f, 0.f};
+  const float fa = ex2((a.m - m) * kLog2e), fb = ex2((b.m - m) * kLog2e);
+  return RowStat{m, a.s * fa + b.s * fb, a.t * fa + b.t * fb};
+}
+
+template <typename T> struct Vec;
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* out) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      out[2 * i] = __uint_as_float(w[i] << 16);
+      out[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float* in) {
+    uint4 v;
+    uint32_t* w = &v.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    __stcs(reinterpret_cast<uint4*>(p), v);
+  }
+  __device__ static float get(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  __device__ static void put(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* out) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  }
+  __device__ static void store(float* p, const float* in) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(in[0], in[1], in[2], in[3]));
+  }
+  __device__ static float get(const float* p) { return *p; }
+  __device__ static void put(float* p, float v) { *p = v; }
+};
+
+// ------------------------------------------------------------------------------------
+// forward: per-row online softmax statistics
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads) row_stats_kernel(const T* __restrict__ logits, int64_t n_rows,
+                                                               int64_t n_cols, int64_t row_stride, float inv_temp,
+                                                               float* __restrict__ stats) {
+  constexpr int V = Vec<T>::N;
+  constexpr int U = 4;  // vectors in flight per thread
+  __shared__ RowStat s_part[kRowThreads / 32];
+  const float c = inv_temp * kLog2e;
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const T* p = logits + row * row_stride;
+    RowStat st{-INFINITY, 0.f, 0.f};
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    const int64_t n_vec = vec_ok ? n_cols / V : 0;
+    for (int64_t v0 = static_cast<int64_t>(threadIdx.x) * U; v0 < n_vec; v0 += static_cast<int64_t>(kRowThreads) * U) {
+      float x[U * V];
+      int cnt = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (v0 + u < n_vec) { Vec<T>::load(p + (v0 + u) * V, x + u * V); cnt = (u + 1) * V; }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < U * V; ++i) if (i < cnt) mx = fmaxf(mx, x[i]);
+      mx *= inv_temp;  // inv_temp > 0
+      if (mx > st.m) {
+        const float f = ex2((st.m - mx) * kLog2e);  // ex2(-inf) = 0 on the first chunk
+        st.s *= f; st.t *= f; st.m = mx;
+      }
+      const float mo = st.m * kLog2e;
+#pragma unroll
+      for (int i = 0; i < U * V; ++i) {
+        if (i < cnt) {
+          const float e = ex2(fmaf(x[i], c, -mo));
+          st.s += e;
+          st.t = fmaf(x[i], e, st.t);
+        }
+      }
+    }
+    // scalar tail (and whole row when the row is not 16-byte aligned)
+    for (int64_t i = n_vec * V + threadIdx.x; i < n_cols; i += kRowThreads) {
+      const float raw = Vec<T>::get(p + i);
+      st = merge(st, RowStat{raw * inv_temp, 1.f, raw});
+    }
+    // block reduction
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      RowStat other{__shfl_xor_sync(0xffffffffu, st.m, o), __shfl_xor_sync(0xffffffffu, st.s, o),
+                    __shfl_xor_sync(0xffffffffu, st.t, o)};
+      st = merge(st, other);
+    }
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = st;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      RowStat r = threadIdx.x < kRowThreads / 32 ? s_part[threadIdx.x] : RowStat{-INFINITY, 0.f, 0.f};
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        RowStat other{__shfl_xor_sync(0xffffffffu, r.m, o), __shfl_xor_sync(0xffffffffu, r.s, o),
+                      __shfl_xor_sync(0xffffffffu, r.t, o)};
+        r = merge(r, other);
+      }
+      if (threadIdx.x == 0)
+        reinterpret_cast<float4*>(stats)[row] = make_float4(r.m, r.s, r.t * inv_temp, 0.f);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void gather_labels_kernel(const T* __restrict__ logits, int64_t n_cols, int64_t row_stride, float inv_temp,
+                                     const int64_t* __restrict__ labels, const int32_t* __restrict__ row_of,
+                                     int64_t n_labels, int64_t vocab_start, float* __restrict__ x_label,
+                                     int64_t x_stride) {
+  for (int64_t m = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; m < n_labels;
+       m += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = row_of ? row_of[m] : m;
+    const int64_t c = labels[m] - vocab_start;
+    float v = 0.f;
+    if (r >= 0 && c >= 0 && c < n_cols) v = Vec<T>::get(logits + r * row_stride + c) * inv_temp;
+    x_label[m * x_stride] = v;
+  }
+}
+
+__global__ void finalize_kernel(const float4* __restrict__ stats_all, int world, int64_t n_rows,
+                                float* __restrict__ logz, float* __restrict__ entropy,
+                                float* __restrict__ x_label_sum) {
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < n_rows;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float m = -INFINITY;
+    for (int w = 0; w < world; ++w) m = fmaxf(m, stats_all[w * n_rows + r].x);
+    float s = 0.f, t = 0.f, xl = 0.f;
+    for (int w = 0; w < world; ++w) {
+      const float4 st = stats_all[w * n_rows + r];
+      xl += st.w;
+      const float f = st.x == -INFINITY ? 0.f : expf(st.x - m);
+      s = fmaf(st.y, f, s);
+      t = fmaf(st.z, f, t);
+    }
+    const float lz = m + logf(s);
+    logz[r] = lz;
+    entropy[r] = lz - t / s;
+    if (x_label_sum) x_label_sum[r] = xl;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads) logprob_bwd_kernel(const T* __restrict__ logits, int64_t n_rows,
+                                                                 int64_t n_cols, int64_t row_stride, float inv_temp,
+                                                                 const float* __restrict__ logz,
+                                                                 const float* __restrict__ entropy,
+                                                                 const float* __restrict__ g_entropy,
+                                                                 const float* __restrict__ g_lp_rowsum,
+                                                                 T* __restrict__ dlogits, int64_t d_row_stride) {
+  constexpr int V = Vec<T>::N;
+  constexpr int U = 4;
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const T* p = logits + row * row_stride;
+    T* q = dlogits + row * d_row_stride;
+    const float lz = logz[row];
+    const float a = g_entropy ? g_entropy[row] : 0.f;
+    const float G = g_lp_rowsum ? g_lp_rowsum[row] : 0.f;
+    // d = inv_temp * p * (a * (-H - lp) - G),  lp = x - lz,  p = e^lp
+    const float k0 = -(a * entropy[row] + G);
+    const float c = inv_temp * kLog2e, lz2 = lz * kLog2e;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(q)) & 15) == 0;
+    const int64_t n_vec = vec_ok ? n_cols / V : 0;
+    for (int64_t v0 = static_cast<int64_t>(threadIdx.x) * U; v0 < n_vec; v0 += static_cast<int64_t>(kRowThreads) * U) {
+      float x[U * V];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v0 + u < n_vec) Vec<T>::load(p + (v0 + u) * V, x + u * V);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (v0 + u < n_vec) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float lp2 = fmaf(x[u * V + i], c, -lz2);  // log2 p
+            const float pr = ex2(lp2);
+            x[u * V + i] = inv_temp * pr * fmaf(-a * kLn2, lp2, k0);
+          }
+          Vec<T>::store(q + (v0 + u) * V, x + u * V);
+        }
+      }
+    }
+    for (int64_t i = n_vec * V + threadIdx.x; i < n_cols; i += kRowThreads) {
+      const float lp2 = fmaf(Vec<T>::get(p + i), c, -lz2);
+      const float pr = ex2(lp2);
+      Vec<T>::put(q + i, inv_temp * pr * fmaf(-a * kLn2, lp2, k0));
+    }
+  }
+}
+
+template <typename T>
+__global__ void bwd_scatter_kernel(T* __restrict__ dlogits, int64_t n_cols, int64_t d_row_stride, float inv_temp,
+                                   const int64_t* __restrict__ labels, const int32_t* __restrict__ row_of,
+                                   const float* __restrict__ g_lp, int64_t n_labels, int64_t vocab_start) {
+  for (int64_t m = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; m < n_labels;
+       m += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = row_of ? row_of[m] : m;
+    const int64_t c = labels[m] - vocab_start;
+    if (r >= 0 && c >= 0 && c < n_cols) {
+      T* p = dlogits + r * d_row_stride + c;
+      Vec<T>::put(p, Vec<T>::get(p) + inv_temp * g_lp[m]);
+    }
+  }
+}
+
+__global__ void rowsum_grad_kernel(const float* __restrict__ g_lp, const int32_t* __restrict__ row_of,
+                                   int64_t n_labels, float* __restrict__ out) {
+  for (int64_t m = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; m < n_labels;
+       m += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = row_of ? row_of[m] : m;
+    if (r >= 0) atomicAdd(out + r, g_lp[m]);
+  }
+}
+
+static int small_grid(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  const int64_t cap = 16 * static_cast<int64_t>(sm_count());
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+static int row_grid(int64_t n_rows) {
+  const int64_t cap = 8 * static_cast<int64_t>(sm_count());  // grid-stride over rows; multiple of SM count
+  return static_cast<int>(n_rows < cap ? n_rows : cap);
+}
+
+}  // namespace dta
+
+using namespace dta;
+
+extern "C" {
+
+int dta_logprob_row_stats(const void* logits, int dtype, int64_t n_rows, int64_t n_cols, int64_t row_stride,
+                          float inv_temperature, float* stats, dta_stream_t stream) {
+  DTA_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
+  DTA_REQUIRE(n_rows >= 0 && n_cols >= 1 && row_stride >= n_cols, "bad logits shape");
+  DTA_REQUIRE(inv_temperature > 0.f, "temperature must be positive");
+  if (n_rows == 0) return DTA_OK;
+  DTA_REQUIRE(logits && stats, "NULL pointer argument");
+  DTA_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 15) == 0, "stats must be 16-byte aligned");
+  if (dtype == 0)
+    row_stats_kernel<__nv_bfloat16><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(logits), n_rows, n_cols, row_stride, inv_temperature, stats);
+  else
+    row_stats_kernel<float><<<row_grid(n_rows), kRowThreads, 0, stream>>>(static_cast<const float*>(logits), n_rows,
+                                                                         n_cols, row_stride, inv_temperature, stats);
+  DTA_CHECK_CUDA(cudaGetLastError());
+  return DTA_OK;
+}
+
+int dta_logprob_gather_labels(const void* logits, int dtype, int64_t n_cols, int64_t row_stride,
+                              float inv_temperature, const int64_t* labels, const int32_t* row_of,
+                              int64_t n_labels, int64_t vocab_start, float* x_label, int64_t x_stride,
+                              dta_stream_t stream) {
+  DTA_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
+  if (n_labels == 0) return DTA_OK;
+  DTA_REQUIRE(logits && labels && x_label && x_stride >= 1, "NULL pointer argument / bad x_stride");
+  if (dtype == 0)
+    gather_labels_kernel<__nv_bfloat16><<<small_grid(n_labels, 256), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(logits), n_cols, row_stride, inv_temperature, labels, row_of, n_labels,
+        vocab_start, x_label, x_stride);
+  else
+    gather_labels_kernel<float><<<small_grid(n_labels, 256), 256, 0, stream>>>(
+        static_cast<const float*>(logits), n_cols, row_stride, inv_temperature, labels, row_of, n_labels,
+        vocab_start, x_label, x_stride);
+  DTA_CHECK_CUDA(cudaGetLastError());
+  return DTA_OK;
+}
+
+int dta_logprob_finalize(const float* stats_all, int world, int64_t n_rows, float* logz, float* entropy,
+                         float* x_label_sum, dta_stream_t stream) {
+  DTA_REQUIRE(world >= 1, "world must be >= 1");
+  if (n_rows == 0) return DTA_OK;
+  DTA_REQUIRE(stats_all && logz && entropy, "NULL pointer argument");
+  finalize_kernel<<<small_grid(n_rows, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(stats_all), world,
+                                                               n_rows, logz, entropy, x_label_sum);
+  DTA_CHECK_CUDA(cudaGetLastError());
+  return DTA_OK;
+}
+
+int dta_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t n_cols, int64_t row_stride,
+                    float inv_temperature, const float* logz, const float* entropy, const float* g_entropy,
+                    const float* g_lp_rowsum, void* dlogits, int64_t d_row_stride, dta_stream_t stream) {
+  DTA_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
+  DTA_REQUIRE(n_rows >= 0 && n_cols >= 1 && row_stride >= n_cols && d_row_stride >= n_cols, "bad logits shape");
+  if (n_rows == 0) return DTA_OK;
+  DTA_REQUIRE(logits && logz && entropy && dlogits, "NULL pointer argument");
+  if (dtype == 0)
+    logprob_bwd_kernel<__nv_bfloat16><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(logits), n_rows, n_cols, row_stride, inv_temperature, logz, entropy,
+        g_entropy, g_lp_rowsum, static_cast<__nv_bfloat16*>(dlogits), d_row_stride);
+  else
+    logprob_bwd_kernel<float><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
+        static_cast<const float*>(logits), n_rows, n_cols, row_stride, inv_temperature, logz, entropy, g_entropy,
+        g_lp_rowsum, static_cast<float*>(dlogits), d_row_stride);
+  DTA_CHECK_CUDA(cudaGetLastError());
+  return DTA_OK;
+}
+
+int dta_logprob_bwd_scatter(void* dlogits, int dtype, int64_t n_cols, int64_t d_row_stride, float inv_temperature,
+                            const int64_t* labels, const int32_t* row_of, const float* g_lp, int64_t n_labels,
+                            int64_t vocab_start, dta_stream_t stream) {
+  DTA_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
+  if (n_labels == 0) return DTA_OK;
+  DTA_REQUIRE(dlogits && labels && g_lp, "NULL pointer argument");
+  if (dtype == 0)
+    bwd_scatter_kernel<__nv_bfloat16><<<small_grid(n_labels, 256), 256, 0, stream>>>(
+        static_cast<__nv_bfloat16*>(dlogits), n_cols, d_row_stride, inv_temperature, labels, row_of, g_lp, n_labels,
+        vocab_start);
+  else
+    bwd_scatter_kernel<float><<<small_grid(n_labels, 256), 256, 0, stream>>>(
+        static_cast<float*>(dlogits), n_cols, d_row_stride, inv_temperature, labels, row_of, g_lp, n_labels,
+        vocab_start);
+  DTA_CHECK_CUDA(cudaGetLastError());
+  return DTA_OK;
+}
+
+int dta_logprob_rowsum_grad(const float* g_lp, const int32_t* row_of, int64_t n_labels, float* g_lp_rowsum,
+                            dta_stream_t stream) {
+  if (n_labels == 0) return DTA_OK;
+  DTA_REQUIRE(g_lp && g_lp_rowsum, "NULL pointer argument");
+  rowsum_grad_kernel<<<small_grid(n_labels, 256), 256, 0, stream>>>(g_lp, row_of, n_labels, g_lp_rowsum);
+  DTA_CHECK_CUDA(cudaGetLastError());
+  return DTA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""Trie-aware K-way load balancing + the NCCL data-parallel step.
+
+Part 1 mirrors the reference module ``data_parallel.py`` (data_parallel.py:8-107):
+``LB_by_n_tokens``, ``LB_by_TM``, ``LB_by_DFS_and_TM`` (+ ``pred_time``,
+``get_original_bins``, ``try_devide``) return K lists of ORIGINAL sequence
+indices, bit-identical to the reference for the same inputs and time model.
+
+Part 2 is new: the reference only writes the bins to disk and replays them
+serially on one GPU (exp/exp_dp.py:45-49).  Here every rank runs its own bin
+through ``TreeTrainingEngine.backward`` and parameter gradients are summed with
+bucketed NCCL all-reduce over NVLink.  The loss is a sum over
+sequences (tree_training_engine.py:396-398), so any partition yields gradients
+that add up to the single-GPU result.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from .token_trie import TokenTrie
+from .trie import CompressedTrie, _get_stats, _get_subtrie
+
+__all__ = [
+    "LB_by_n_tokens", "LB_by_TM", "LB_by_DFS_and_TM", "pred_time", "get_original_bins",
+    "try_devide", "partition", "allreduce_gradients", "dp_backward",
+]
+
+
+# --------------------------------------------------------------------------
+# Part 1 — partitioners (reference semantics)
+# --------------------------------------------------------------------------
+def _argmin_first(values: Sequence[float]) -> int:
+    best = 0
+    for j in range(1, len(values)):
+        if values[j] < values[best]:
+            best = j
+    return best
+
+
+def LB_by_n_tokens(token_seqs, K: int) -> List[List[int]]:
+    """Greedy longest-first packing on raw token counts (data_parallel.py:8-16)."""
+    bins: List[List[int]] = [[] for _ in range(K)]
+    load = [0] * K
+    for i in sorted(range(len(token_seqs)), key=lambda i: -len(token_seqs[i])):
+        j = _argmin_first(load)
+        bins[j].append(i)
+        load[j] += len(token_seqs[i])
+    return bins
+
+
+def pred_time(compressed_trie: CompressedTrie, time_model, mode: str,
+              block_size: Optional[int] = None) -> float:
+    """Predicted step time of a (sub-)trie in its planned leaf order (data_parallel.py:18-27)."""
+    if mode == "forward":
+        _, lens, lcp_lens = compressed_trie.get_order_forward()
+    elif mode == "backward":
+        _, lens, lcp_lens = compressed_trie.get_order_backward()
+    else:
+        raise ValueError(f"Unsupported mode: {mode}")
+    return time_model.pred(_get_stats(lens, lcp_lens, mode, block_size))
+
+
+def get_original_bins(token_trie: TokenTrie, leaf_bins: List[List[int]]) -> List[List[int]]:
+    """Leaf indices -> original sequence indices via the attach lists (data_parallel.py:29-37)."""
+    return [
+        [attach["_sequence_batch_id"] for leaf in leaf_bin for attach, _ in token_trie.attach_lists[leaf]]
+        for leaf_bin in leaf_bins
+    ]
+
+
+def LB_by_TM(token_seqs, time_model, args) -> List[List[int]]:
+    """Greedy: next leaf (DFS order) goes to the bin with least predicted time (data_parallel.py:39-56)."""
+    token_trie = TokenTrie(token_seqs)
+    full = CompressedTrie(token_trie.lens, token_trie.lcp_lens)
+    K = args.K
+    leaf_bins: List[List[int]] = [[] for _ in range(K)]
+    bin_time = [0.0] * K
+    for leaf in range(len(token_trie.inputs)):
+        j = _argmin_first(bin_time)
+        leaf_bins[j].append(leaf)
+        bin_time[j] = pred_time(_get_subtrie(full, leaf_bins[j]), time_model, args.mode, args.block_size)
+    return get_original_bins(token_trie, leaf_bins)
+
+
+def try_devide(compressed_trie, n_seqs, args, divL, divR, time_model, cost_limit: float):
+    """Cut DFS-ordered leaves into consecutive runs of predicted cost <= cost_limit.
+
+    Returns the run start indices; more than K of them means the limit is
+    infeasible.  ``divL``/``divR`` bracket each cut from earlier probes
+    (data_parallel.py:58-79).
+    """
+    K = args.K
+    cuts: List[int] = []
+    start = 0
+    while start < n_seqs:
+        cuts.append(start)
+        if len(cuts) > K:
+            break
+        lo = max(divL[len(cuts)] - 1, start)
+        hi = divR[len(cuts)] - 1
+        while lo < hi:
+            mid = (lo + hi + 1) // 2
+            sub = _get_subtrie(compressed_trie, set(range(start, mid + 1)))
+            if pred_time(sub, time_model, args.mode, args.block_size) <= cost_limit:
+                lo = mid
+            else:
+                hi = mid - 1
+        start = lo + 1
+    return cuts
+
+
+def LB_by_DFS_and_TM(token_seqs, time_model, args) -> List[List[int]]:
+    """Contiguous DFS ranges with minimal predicted makespan (data_parallel.py:81-107).
+
+    Outer bisection on the per-bin cost limit between total/K and total, to
+    1e-4 of the total; each probe is ``try_devide``.
+    """
+    token_trie = TokenTrie(token_seqs)
+    n_leaf = len(token_trie.inputs)
+    full = CompressedTrie(token_trie.lens, token_trie.lcp_lens)
+
+    K = args.K
+    hi = float(pred_time(full, time_model, args.mode, args.block_size))
+    lo = hi / K
+    eps = hi * 1e-4
+
+    divL = [0] * (K + 1)
+    divR = [n_leaf] * (K + 1)
+    while hi - lo > eps:
+        mid = (lo + hi) / 2.0
+        cuts = try_devide(full, n_leaf, args, divL, divR, time_model, mid)
+        if len(cuts) <= K:
+            hi = mid
+            divR[: len(cuts)] = cuts
+        else:
+            lo = mid + eps
+            divL = cuts[: K + 1]
+
+    leaf_bins = [list(range(divR[i], divR[i + 1])) for i in range(K)]
+    return get_original_bins(token_trie, leaf_bins)
+
+
+def partition(token_seqs, K: int, method: str = "LB_by_DFS_and_TM", time_model=None,
+              mode: str = "backward", block_size: Optional[int] = None) -> List[List[int]]:
+    """Convenience front-end: pick a partitioner by the reference's CLI names."""
+    from .tree_time_model import TreeTimeModel
+    tm = time_model if time_model is not None else TreeTimeModel()
+    args = SimpleNamespace(K=K, mode=mode, block_size=block_size)
+    if method == "LB_by_n_tokens":
+        return LB_by_n_tokens(token_seqs, K)
+    if method == "LB_by_TM":
+        return LB_by_TM(token_seqs, tm, args)
+    if method == "LB_by_DFS_and_TM":
+        return LB_by_DFS_and_TM(token_seqs, tm, args)
+    raise ValueError(f"Unsupported method: {method}")
+
+
+# --------------------------------------------------------------------------
+# Part 2 — data-parallel runtime (new; one process per GPU, NCCL over NVLink)
+# --------------------------------------------------------------------------
+def allreduce_gradients(model: torch.nn.Module, group=None, bucket_bytes: int = 256 << 20) -> None:
+    """Sum ``param.grad`` over ranks with bucketed all-reduce.
+
+    NVSwitch gives every GPU full bandwidth to every peer, so buckets are sized
+    for launch latency (few, large) rather than link count.  Parameters whose
+    grad is None on this rank (empty bin) contribute zeros.
+    """
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    params = [p for p in model.parameters() if p.requires_grad]
+    by_dtype = {}
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        by_dtype.setdefault(p.grad.dtype, []).append(p)
+    for plist in by_dtype.values():
+        bucket, size = [], 0
+        for p in plist + [None]:
+            if p is not None:
+                bucket.append(p)
+                size += p.grad.numel() * p.grad.element_size()
+            if bucket and (p is None or size >= bucket_bytes):
+                flat = torch.cat([q.grad.reshape(-1) for q in bucket])
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+                off = 0
+                for q in bucket:
+                    n = q.grad.numel()
+                    q.grad.copy_(flat[off:off + n].view_as(q.grad))
+                    off += n
+                bucket, size = [], 0
+
+
+def dp_backward(engine, model, token_seqs, attachs, loss_fn: Callable, *, bins=None,
+                method: str = "LB_by_DFS_and_TM", time_model=None, block_size: Optional[int] = 2048,
+                group=None, permute: str = "ours") -> float:
+    """One data-parallel training step over a global batch of sequences.
+
+    Every rank computes the SAME partition (deterministic host code, no
+    broadcast needed), runs its bin through ``engine.backward`` and joins the
+    gradient all-reduce.  Returns the global loss (sum over ranks).
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if bins is None:
+        bins = partition(token_seqs, world, method, time_model, "backward", block_size) if world > 1 \
+            else [list(range(len(token_seqs)))]
+    mine = bins[rank]
+    loss = 0.0
+    if mine:
+        trie = TokenTrie([token_seqs[i] for i in mine], [dict(attachs[i]) for i in mine])
+        if permute == "ours":
+            trie.backward_permute()
+        loss = engine.backward(model, trie, loss_fn, block_size=block_size)
+    allreduce_gradients(model, group)
+    if world > 1:
+        t = torch.tensor([loss], dtype=torch.float64, device=next(model.parameters()).device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        loss = float(t.item())
+    return loss

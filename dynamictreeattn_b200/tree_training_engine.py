@@ -1,0 +1,269 @@
+"""TreeTrainingEngine — forward / backward over a TokenTrie in ONE linearised pass.
+
+Drop-in for the reference class (tree_training_engine.py:52-616): same constructor,
+``forward(model, token_trie) -> List[Tensor]`` and
+``backward(model, token_trie, loss_fn, block_size, cut_f1_tail) -> float`` with the
+same conventions (per-sequence fp32 log-probs of length ``len(seq)-1``; gradients are
+ACCUMULATED into ``param.grad``; the returned loss is a Python float).
+
+What runs is different.  The reference walks the trie with a push/pop KV stack, calls
+the HF model once or twice per leaf and stitches the backward from injected gradients
+(tree_training_engine.py:146-313, 315-487, 555-616).  Here the trie is linearised once
+on the GPU (``linearize.py``: parent / depth / ancestor intervals), the model trunk runs
+ONCE over all N trie tokens with ``position_ids = depth`` and the ancestor-masked tcgen05
+attention kernels, and the vocabulary head is evaluated in row chunks by the fused
+log-prob/entropy kernels with per-EDGE labels (a fork node has one label per child,
+which is why the reference keeps whole logits rows at fork positions,
+tree_training_engine.py:217-220, 369-372).  The result is mathematically the reference's
+ and independent of ``block_size`` / ``cut_f1_tail`` / leaf order,
+which are accepted for compatibility: ``block_size`` only sizes the head's row chunks.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+
+from . import _cabi
+from .attention import use_tree_attention
+from .linearize import TrieLayout, linearize_trie
+from .vocab_parallel import logprob_entropy_rows, logprob_entropy_rows_backward
+
+__all__ = ["TreeTrainingEngine", "_get_forkpos"]
+
+
+def _get_forkpos(lens, lcp_lens, block_size) -> list:
+    """Stack positions whose full logits row the REFERENCE engine must retain
+    (tree_training_engine.py:12-49): ``lcp-1`` of every fork plus ``pop_start-1`` of every
+    block boundary.  The single-pass engine needs no such bookkeeping (every row's labels
+    are known up front); kept for API parity and for the cost-model tests."""
+    out = set()
+    for lcp in lcp_lens:
+        if lcp > 0:
+            out.add(lcp - 1)
+    if block_size is not None:
+        for i, end in enumerate(lens):
+            start = 0 if i == len(lcp_lens) else lcp_lens[i]
+            n = end - start
+            n_blocks = -(-n // block_size)
+            blk = -(-n // n_blocks)
+            for b in range(n_blocks):
+                cut = max(end - (b + 1) * blk, start)
+                if cut > 0:
+                    out.add(cut - 1)
+    return sorted(out)
+
+
+def _decoder_and_head(model):
+    """(trunk returning last_hidden_state, lm_head weight [V, H])."""
+    trunk = getattr(model, "model", None)
+    if trunk is None and hasattr(model, "get_decoder"):
+        trunk = model.get_decoder()
+    head = model.get_output_embeddings() if hasattr(model, "get_output_embeddings") else model.lm_head
+    if trunk is None or head is None:
+        raise _cabi.DtaError("model must expose .model (decoder trunk) and an lm_head")
+    if getattr(head, "bias", None) is not None:
+        raise _cabi.DtaError("lm_head with bias is not supported")
+    return trunk, head.weight
+
+
+_MM_OUT_DTYPE = None
+
+
+def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a @ b with fp32 output (one rounding at the very end of the dW accumulation); falls back
+    to a bf16-output GEMM per chunk on torch builds without ``out_dtype``."""
+    global _MM_OUT_DTYPE
+    if _MM_OUT_DTYPE is None:
+        try:
+            torch.mm(a[:1], b[:, :1], out_dtype=torch.float32)
+            _MM_OUT_DTYPE = True
+        except (TypeError, RuntimeError):
+            _MM_OUT_DTYPE = False
+    if _MM_OUT_DTYPE:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    return torch.mm(a, b).float()
+
+
+class _EdgePlan:
+    """Edges (parent row -> child node) grouped by parent row, so a chunk of logits rows
+    maps to one contiguous run of labels."""
+
+    def __init__(self, layout: TrieLayout):
+        N = layout.n_nodes
+        parent = layout.parent[:N]
+        child = torch.nonzero(parent >= 0).squeeze(1)
+        rows = parent[child].to(torch.int64)
+        order = torch.argsort(rows, stable=True)
+        self.child = child[order]                      # node that receives the log-prob
+        self.row = rows[order]                         # logits row the label is read from
+        self.label = layout.tok[self.child]            # token of the child
+        self.n_nodes = N
+
+    def span(self, a: int, b: int) -> Tuple[int, int]:
+        bounds = torch.searchsorted(self.row, torch.tensor([a, b], device=self.row.device))
+        e0, e1 = bounds.tolist()
+        return e0, e1
+
+
+class _TreeHeadLoss(torch.autograd.Function):
+    """loss(hidden, W) = sum_seq loss_fn(lp[path[1:L]], H[path[:L]], attach).
+
+    Forward evaluates the head in row chunks (logits = hidden W^T, fused stats kernel),
+    runs the user's ``loss_fn`` on the small per-node vectors, and — because the head is
+    the last op before the scalar loss — already produces d loss / d hidden and d loss / dW
+    chunk by chunk (logits recomputed, gradient written in place over them), so no
+    ``[N, V]`` tensor outlives a chunk.  Backward just scales the stashed gradients.
+    """
+
+    @staticmethod
+    def forward(ctx, hidden: torch.Tensor, weight: torch.Tensor, engine, layout: TrieLayout, token_trie, loss_fn,
+                chunk_rows: int):
+        N = layout.n_nodes
+        h = hidden.detach()
+        W = weight.detach()
+        lp_nodes, ent_nodes, logz, plan = engine._head_forward(h, W, layout, chunk_rows)
+
+        # ---- user loss on per-node vectors (tiny autograd graph) --------------------------
+        with torch.enable_grad():
+            lp_leaf = lp_nodes.requires_grad_(True)
+            ent_leaf = ent_nodes.clone().requires_grad_(True)
+            total = None
+            for i, attach_list in enumerate(token_trie.attach_lists):
+                for attach, length in attach_list:
+                    path = layout.path_of_leaf(i, length).long()
+                    term = loss_fn(lp_leaf[path[1:]], ent_leaf[path], attach)
+                    total = term if total is None else total + term
+            if total is None:
+                total = lp_leaf.sum() * 0.0
+            g_lp, g_ent = torch.autograd.grad(total, [lp_leaf, ent_leaf], allow_unused=True)
+        loss = total.detach()
+
+        # ---- head backward, chunked -------------------------------------------------------
+        need_h = hidden.requires_grad
+        need_w = weight.requires_grad
+        dh = torch.empty_like(h) if need_h else None
+        dW32 = torch.zeros(W.shape, dtype=torch.float32, device=W.device) if need_w else None
+        if need_h or need_w:
+            g_lp = torch.zeros_like(lp_nodes) if g_lp is None else g_lp.float()
+            g_ent = torch.zeros_like(ent_nodes) if g_ent is None else g_ent.float()
+            for a in range(0, N, chunk_rows):
+                b = min(a + chunk_rows, N)
+                e0, e1 = plan.span(a, b)
+                logits = h[a:b] @ W.t()
+                row_of = (plan.row[e0:e1] - a).to(torch.int32)
+                logprob_entropy_rows_backward(logits, plan.label[e0:e1], row_of, 1.0, 0, logz[a:b], ent_nodes[a:b],
+                                              g_lp[plan.child[e0:e1]], g_ent[a:b], out=logits)
+                if need_h:
+                    torch.mm(logits, W, out=dh[a:b])
+                if need_w:
+                    dW32.add_(_mm_f32(logits.t(), h[a:b]))
+                del logits
+        ctx.dh = dh
+        ctx.dW = dW32.to(W.dtype) if need_w else None
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dh = ctx.dh * g.to(ctx.dh.dtype) if ctx.dh is not None else None
+        dW = ctx.dW * g.to(ctx.dW.dtype) if ctx.dW is not None else None
+        ctx.dh = ctx.dW = None
+        return dh, dW, None, None, None, None, None
+
+
+class TreeTrainingEngine:
+    """Engine for forward / backward computation over sequences with shared prefixes."""
+
+    def __init__(self, model_config, device, dtype: torch.dtype, max_seq_len: int, forward_only: bool = False):
+        self.model = None
+        self.model_config = model_config
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.max_seq_len = max_seq_len
+        self.forward_only = forward_only
+        # fields the reference reads (tree_training_engine.py:102-106); validated early
+        self.n_layers = model_config.num_hidden_layers
+        self.n_kv_heads = model_config.num_key_value_heads
+        self.head_dim = model_config.head_dim if hasattr(model_config, "head_dim") and model_config.head_dim \
+            else model_config.hidden_size // model_config.num_attention_heads
+        self.head_chunk_rows = 8192
+        self.last_layout: Optional[TrieLayout] = None
+
+    # ---- shared pieces ---------------------------------------------------------------------
+    def _check_lengths(self, token_trie) -> None:
+        for ids in token_trie.inputs:
+            n = int(ids.numel())
+            assert n <= self.max_seq_len, (
+                f"Exceeds max_seq_len: cur_len=0, new_tokens={n}, max={self.max_seq_len}")
+
+    def _trunk(self, model, layout: TrieLayout) -> torch.Tensor:
+        trunk, _ = _decoder_and_head(model)
+        N = layout.n_nodes
+        with use_tree_attention(model, layout):
+            out = trunk(input_ids=layout.tok.unsqueeze(0),
+                        position_ids=layout.depth[:N].to(torch.int64).unsqueeze(0),
+                        use_cache=False)
+        return out.last_hidden_state[0]                       # [N, hidden]
+
+    def _head_forward(self, h: torch.Tensor, W: torch.Tensor, layout: TrieLayout, chunk_rows: int):
+        """Per-node log-prob of the edge INTO the node (roots: 0) and per-node entropy."""
+        N = layout.n_nodes
+        dev = h.device
+        plan = _EdgePlan(layout)
+        lp_nodes = torch.zeros(N, dtype=torch.float32, device=dev)
+        ent_nodes = torch.empty(N, dtype=torch.float32, device=dev)
+        logz = torch.empty(N, dtype=torch.float32, device=dev)
+        for a in range(0, N, chunk_rows):
+            b = min(a + chunk_rows, N)
+            e0, e1 = plan.span(a, b)
+            logits = h[a:b] @ W.t()
+            row_of = (plan.row[e0:e1] - a).to(torch.int32)
+            x_label, lz, ent = logprob_entropy_rows(logits, plan.label[e0:e1], row_of, 1.0)
+            lp_nodes[plan.child[e0:e1]] = x_label - lz[row_of.long()]
+            ent_nodes[a:b] = ent
+            logz[a:b] = lz
+            del logits
+        return lp_nodes, ent_nodes, logz, plan
+
+    def _chunk_rows(self, block_size: Optional[int]) -> int:
+        rows = self.head_chunk_rows
+        if block_size is not None and block_size > 0:
+            rows = max(rows, int(block_size))
+        return rows
+
+    # ---- public API ------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, model, token_trie) -> List[torch.Tensor]:
+        """Per-sequence log-probs, indexed by ``attach['_sequence_batch_id']``
+        (reference tree_training_engine.py:515-553)."""
+        self.model = model
+        self._check_lengths(token_trie)
+        returns: List[Optional[torch.Tensor]] = [None] * token_trie.n_sequences
+        if not token_trie.inputs:
+            return returns
+        layout = linearize_trie(token_trie, self.device)
+        self.last_layout = layout
+        h = self._trunk(model, layout)
+        _, W = _decoder_and_head(model)
+        lp_nodes, _, _, _ = self._head_forward(h, W, layout, self.head_chunk_rows)
+        for i, attach_list in enumerate(token_trie.attach_lists):
+            for attach, length in attach_list:
+                path = layout.path_of_leaf(i, length).long()
+                returns[attach["_sequence_batch_id"]] = lp_nodes[path[1:]].clone()
+        return returns
+
+    def backward(self, model, token_trie, loss_fn: Callable, block_size: Optional[int] = 2048,
+                 cut_f1_tail: bool = True) -> float:
+        """Accumulate d(sum of per-sequence losses)/d(params) into ``param.grad``; return the loss
+        (reference tree_training_engine.py:555-616)."""
+        self.model = model
+        self._check_lengths(token_trie)
+        if not token_trie.inputs:
+            return 0.0
+        layout = linearize_trie(token_trie, self.device)
+        self.last_layout = layout
+        h = self._trunk(model, layout)
+        _, W = _decoder_and_head(model)
+        loss = _TreeHeadLoss.apply(h, W, self, layout, token_trie, loss_fn, self._chunk_rows(block_size))
+        loss.backward()
+        return float(loss.item())

@@ -1,0 +1,164 @@
+/* dta_b200.h — C ABI of the B200-native DynamicTreeAttn hot path (libdta_b200.so).
+ *
+ * The reference (Whisper-6/DynamicTreeAttn) is pure Python and has no FFI layer of its
+ * own; each entry point below names the reference code whose work it
+ * replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked HOST;
+ *   - the caller owns all memory, including workspaces (sizes from *_workspace_bytes);
+ *   - every call is asynchronous on `stream` and returns 0 on success, else a non-zero
+ *     code whose text is available from dta_last_error() (thread-local);
+ *   - no torch types, no C++ types, no exceptions cross this boundary;
+ *   - there is NO CPU fallback: without a sm_100a device the calls fail.
+ *
+ * Linearised trie ("layout") vocabulary, SURVEY.md §9:
+ *   node n = one trie token, numbered in DFS push order; N = n_nodes; n_pad = N rounded up
+ *   to a multiple of DTA_TILE; depth[n] = position id; parent[n] = node one level up (-1 at a
+ *   root); subtree_end[n] = first node after n's subtree, so key k is visible to query q
+ *   iff k <= q < subtree_end[k].
+ */
+#ifndef DTA_B200_H
+#define DTA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTA_ABI_VERSION 1
+#define DTA_TILE 128 /* attention tile edge (queries and keys) */
+
+typedef struct CUstream_st* dta_stream_t;
+
+const char* dta_last_error(void);
+int dta_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Trie indexing (integer, bit-exact with the reference)
+ * ------------------------------------------------------------------------------------- */
+
+/* Longest common prefix of every adjacent pair of n_seq sequences stored back to back in
+ * `tokens` (sequence i = tokens[seq_off[i] .. seq_off[i+1])), plus a sortedness check:
+ * *unsorted_flag is set to 1 if some pair is out of lexicographic order.
+ * Replaces _lcp_torch / the LCP loop of _leafization (reference token_trie.py:6-10, 22-30). */
+int dta_lcp_adjacent(const int64_t* tokens, const int64_t* seq_off, int n_seq, int32_t* lcp_out,
+                     int32_t* unsorted_flag, dta_stream_t stream);
+
+/* Workspace for dta_trie_linearize / dta_trie_paths (sparse tables over the fork depths). */
+size_t dta_trie_workspace_bytes(int n_leaf);
+
+/* DFS linearisation of the trie given by (lens[n_leaf], lcp[n_leaf-1]) — the push order of
+ * the reference engine (reference tree_training_engine.py:541-546, 588-594).
+ * Outputs: leaf_off[n_leaf+1] (exclusive warp-scan of new tokens per leaf; last = N),
+ * depth[n_pad], parent[n_pad], subtree_end[n_pad], leaf_of[n_pad]; entries >= N are
+ * padding (depth 0, parent -1, subtree_end 0, leaf_of -1).  n_nodes must equal
+ * sum(lens) - sum(lcp). */
+int dta_trie_linearize(const int32_t* lens, const int32_t* lcp, int n_leaf, int n_nodes, int n_pad,
+                       int32_t* leaf_off, int32_t* depth, int32_t* parent, int32_t* subtree_end,
+                       int32_t* leaf_of, void* workspace, dta_stream_t stream);
+
+/* Root-to-leaf node ids: path[path_off[i] + d] = node at depth d on leaf i's path, d < lens[i]
+ * (the stack slots the reference slices as logprobs[:L-1] / entropy[:L],
+ * reference tree_training_engine.py:225-228, 397-398).  path_off = exclusive scan of lens.
+ * Must run after dta_trie_linearize with the same workspace. */
+int dta_trie_paths(const int32_t* lens, const int32_t* lcp, const int32_t* leaf_off, int n_leaf,
+                   const int64_t* path_off, int64_t total, int32_t* path, const void* workspace,
+                   dta_stream_t stream);
+
+/* Per-tile mask summaries and work orders for the attention kernels (n_tiles = n_pad/DTA_TILE):
+ *   kmax_end[t], kmin_end[t] : max / min of subtree_end over the VALID keys of tile t
+ *   q_order[n_tiles]         : query tiles sorted by number of live key tiles, descending
+ *   q_nlive[n_tiles]         : that number, indexed by tile
+ *   k_order[n_tiles]         : key tiles sorted by number of live query tiles, descending
+ *   k_qlast[n_tiles]         : last live query tile of key tile t (live range is [t, k_qlast[t]])
+ *   pair_count[1] (int64)    : number of visible (q,k) pairs = sum(depth)+N */
+int dta_tile_meta(const int32_t* subtree_end, const int32_t* depth, int n_nodes, int n_pad,
+                  int32_t* kmax_end, int32_t* kmin_end, int32_t* q_order, int32_t* q_nlive, int32_t* k_order,
+                  int32_t* k_qlast, int64_t* pair_count, dta_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Tree attention (bf16 in, fp32 accumulate) — replaces the per-push/per-pop HF attention
+ * calls against the KV stack (reference tree_training_engine.py:182-186, 248-252, 351-353;
+ * HF models/qwen3/modeling_qwen3.py:273-287) by ONE ancestor-masked pass per layer.
+ * Layout: q/out/dq [N, Hq, D], k/v/dk/dv [N, Hkv, D] with arbitrary row/head strides
+ * (elements), D contiguous; D must be 128; Hq % Hkv == 0.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_nodes, n_pad;
+  int32_t n_q_heads, n_kv_heads, head_dim;
+  int64_t q_row_stride, q_head_stride;
+  int64_t k_row_stride, k_head_stride;
+  int64_t v_row_stride, v_head_stride;
+  int64_t o_row_stride, o_head_stride;
+  float scale; /* softmax scale, normally head_dim^-0.5 */
+} dta_attn_shape_t;
+
+typedef struct {
+  const int32_t* subtree_end; /* [n_pad] */
+  const int32_t* kmax_end;    /* [n_tiles] */
+  const int32_t* kmin_end;    /* [n_tiles] */
+  const int32_t* q_order;     /* [n_tiles] */
+  const int32_t* k_order;     /* [n_tiles] */
+  const int32_t* k_qlast;     /* [n_tiles] */
+} dta_attn_meta_t;
+
+/* out[N,Hq,D] bf16 (o strides), lse[Hq, n_pad] fp32 (natural-log sum-exp of scaled scores). */
+int dta_tree_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
+                      const dta_attn_meta_t* meta, const dta_attn_shape_t* shape, dta_stream_t stream);
+
+/* Workspace: fp32 dq accumulator [N,Hq,D] + delta [Hq,n_pad]. */
+size_t dta_tree_attn_bwd_workspace_bytes(const dta_attn_shape_t* shape);
+
+/* dout uses the o strides; dq uses the q strides, dk the k strides, dv the v strides. */
+int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                      const float* lse, void* dq, void* dk, void* dv, const dta_attn_meta_t* meta,
+                      const dta_attn_shape_t* shape, void* workspace, dta_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Log-prob + entropy over a vocab shard — replaces _gather_logprobs[_entropy] and the
+ * vocab-parallel autograd functions (reference vocab_parallel.py:13-27, 117-166, 249-321,
+ * 324-370).  x = logit * inv_temperature.  dtype: 0 = bf16, 1 = fp32.
+ * ------------------------------------------------------------------------------------- */
+
+/* One pass over logits[n_rows, n_cols] (row_stride elements): stats[r] = {m, sum e^(x-m),
+ * sum x e^(x-m), 0} for this shard.  These 16 bytes per row are what ranks exchange. */
+int dta_logprob_row_stats(const void* logits, int dtype, int64_t n_rows, int64_t n_cols, int64_t row_stride,
+                          float inv_temperature, float* stats, dta_stream_t stream);
+
+/* x_label[m * x_stride] = x[row_of[m]][labels[m] - vocab_start] if the label falls in this shard
+ * else 0.  row_of == NULL means row_of[m] = m.  row_of[m] < 0 yields 0 (root nodes have no
+ * edge).  With one label per row, x_label = stats + 3 and x_stride = 4 packs the value into the
+ * spare word of the row statistics, so a vocab-parallel rank exchanges 16 bytes per row in all. */
+int dta_logprob_gather_labels(const void* logits, int dtype, int64_t n_cols, int64_t row_stride,
+                              float inv_temperature, const int64_t* labels, const int32_t* row_of,
+                              int64_t n_labels, int64_t vocab_start, float* x_label, int64_t x_stride,
+                              dta_stream_t stream);
+
+/* Merge `world` shard statistics (stats_all[world, n_rows, 4]) with the online-softmax rule:
+ * logz[r] = log sum_v e^x, entropy[r] = logz - E_p[x]; if x_label_sum != NULL it receives the sum
+ * over shards of the 4th statistics word (the label logit packed by dta_logprob_gather_labels). */
+int dta_logprob_finalize(const float* stats_all, int world, int64_t n_rows, float* logz, float* entropy,
+                         float* x_label_sum, dta_stream_t stream);
+
+/* dlogits[r,c] = inv_temperature * p * ( g_entropy[r] * (-entropy[r] - log p) - g_lp_rowsum[r] ),
+ * p = e^(x - logz[r]); written in `dtype`; dlogits may alias logits (in place).
+ * g_lp_rowsum[r] = sum of g_lp over the labels attached to row r.  Either grad may be NULL. */
+int dta_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t n_cols, int64_t row_stride,
+                    float inv_temperature, const float* logz, const float* entropy, const float* g_entropy,
+                    const float* g_lp_rowsum, void* dlogits, int64_t d_row_stride, dta_stream_t stream);
+
+/* dlogits[row_of[m]][labels[m]-vocab_start] += inv_temperature * g_lp[m] for labels in the shard.
+ * (row, label) pairs must be unique — true for trie edges and for one label per row. */
+int dta_logprob_bwd_scatter(void* dlogits, int dtype, int64_t n_cols, int64_t d_row_stride,
+                            float inv_temperature, const int64_t* labels, const int32_t* row_of,
+                            const float* g_lp, int64_t n_labels, int64_t vocab_start, dta_stream_t stream);
+
+/* g_lp_rowsum[row_of[m]] += g_lp[m] (caller zero-fills g_lp_rowsum). */
+int dta_logprob_rowsum_grad(const float* g_lp, const int32_t* row_of, int64_t n_labels, float* g_lp_rowsum,
+                            dta_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTA_B200_H */
