@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — trie tokens/s, fwd+bwd, Qwen3-0.6B on a tau2-16k-shaped merged trie (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Our arm (default).  One "step" = one pass of the hot path over one batch of synthetic tries:
+trunk forward with the tcgen05 tree-attention kernels, fused logprob/entropy head, loss,
+full backward (attention bwd kernels, head bwd kernel), gradients accumulated into param.grad.
+  value     = device-resident throughput: the trie layout (tokens, parent/depth/intervals, tile
+              metadata) is already in HBM when the timed region starts; CUDA events, max over ranks.
+  e2e       = the same metric through the public API with HOST inputs: TokenTrie(host tensors) ->
+              backward_permute -> TreeTrainingEngine.backward -> float loss, i.e. host trie build,
+              pinned H2D of the tokens/plan, linearisation kernels and the D2H loss read are inside
+              the timed region every step.
+  roofline  = tree-attention BACKWARD main kernel (the dominant kernel): algorithmic FLOPs per launch
+              (pairs * Hq * D * 10) / mean launch duration from CUDA events recorded around the
+              kernel inside the C library, against MEASURED_PEAKS.json bf16_tflops_sustained.
+  N > 1     = weak scaling: N independent tries (seeds 0..N-1), partitioned over ranks with the
+              reference's LB_by_DFS_and_TM driven by a TreeTimeModel calibrated on this box, one bin
+              per rank, NCCL gradient all-reduce inside the timed region.
+Reference arm (--impl reference).  The reference's algorithm (DFS over the trie with a KV stack)
+as restated in oracle/tree_oracle.py, fp32 on the host cores with all threads, on a bounded sample
+of the same generator (the reference itself is not present on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
+
+import torch  # noqa: E402
+
+METRIC = "trie_tokens_per_sec_fwd_bwd"
+UNIT = "trie tokens/s"
+ATTACH = {"w_logprobs": -1.0, "w_entropy": 0.1}          # reference run.py:196
+
+
+def example_loss(logprob, entropy, attach):
+    """The loss of the reference's own drivers (run.py:149-152)."""
+    return attach["w_logprobs"] * logprob.mean() + attach["w_entropy"] * entropy.mean()
+
+
+def qwen3_0p6b_config():
+    from transformers import Qwen3Config
+    return Qwen3Config(vocab_size=151936, hidden_size=1024, intermediate_size=3072, num_hidden_layers=28,
+                       num_attention_heads=16, num_key_value_heads=8, head_dim=128,
+                       max_position_embeddings=40960, rms_norm_eps=1e-6, rope_theta=1000000.0,
+                       tie_word_embeddings=True)
+
+
+def tau2_trie(seed: int):
+    """trunk 6144, fan-out (4,2,2), segments U{1024..3072}, depth <= 16384."""
+    from trie_cases import synth_trie
+    return synth_trie(seed, 6144, (4, 2, 2), (1024, 3072), vocab=151936, max_depth=16384)
+
+
+def cpu_sample_trie(seed: int):
+    """Bounded sample of the same generator for the CPU legs (~2k trie tokens)."""
+    from trie_cases import synth_trie
+    return synth_trie(seed, 512, (2, 2), (128, 384), vocab=151936, max_depth=16384)
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0)), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in Path(self.path).read_text().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 8]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({names[i] for r in rows if len(r) >= 8 for i in range(4) if "Active" in r[4 + i]
+                              and "Not" not in r[4 + i]})
+            if sm:
+                out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                       "samples": len(sm), "power_w_max": max(float(r[3]) for r in rows if len(r) >= 8)}
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's restatement of the reference algorithm on host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, seed: int = 0):
+    from transformers import Qwen3ForCausalLM
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    from oracle import tree_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = Qwen3ForCausalLM(qwen3_0p6b_config()).float()
+    model.config._attn_implementation = "sdpa"
+    seqs = cpu_sample_trie(seed)
+    times, n_tok = [], 0
+    for it in range(warmup + steps):
+        trie = TokenTrie(seqs, [dict(ATTACH) for _ in seqs])
+        trie.backward_permute()
+        n_tok = trie.get_stats("forward")["n_tree_tokens"]
+        t0 = time.perf_counter()
+        tree_oracle.tree_stack_backward(model, trie.inputs, trie.lcp_lens, trie.attach_lists, tree_oracle.example_loss)
+        dt = time.perf_counter() - t0
+        model.zero_grad(set_to_none=True)
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    sample = (f"oracle/tree_oracle.tree_stack_backward, Qwen3-0.6B-shaped random-init fp32, synth trie "
+              f"(trunk 512, fan (2,2), seg U{{128..384}}) = {n_tok} trie tokens / {sum(len(s) for s in seqs)} "
+              f"sequence tokens per step")
+    return {"value": n_tok * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+            "sample": sample, "n_tok": n_tok}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)   # bounded: each step is ~1 min of CPU work
+    r = cpu_reference_run(steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "qwen3-0.6b tau2-16k-shaped merged trie, fwd+bwd (bounded CPU sample)",
+                   "inputs_vs_l2": "n/a (host)"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from transformers import Qwen3ForCausalLM
+    from dynamictreeattn_b200 import _cabi, attention
+    from dynamictreeattn_b200.data_parallel import allreduce_gradients, partition
+    from dynamictreeattn_b200.linearize import linearize_trie
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    from dynamictreeattn_b200.tree_time_model import TreeTimeModel
+    from dynamictreeattn_b200.tree_training_engine import TreeTrainingEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.load(build_if_missing=False)
+    peak_tflops, peak_gbs, peak_src = load_peaks()
+
+    cfg = qwen3_0p6b_config()
+    torch.manual_seed(0)
+    model = Qwen3ForCausalLM(cfg).to(dev, torch.bfloat16)
+    model.train()
+    engine = TreeTrainingEngine(cfg, dev, torch.bfloat16, 16384)
+
+    # ---- workload: one tau2-shaped trie per GPU (weak scaling); global batch partitioned by the cost model
+    seqs_global = []
+    for s in range(world):
+        seqs_global += tau2_trie(s)
+    attach_global = [dict(ATTACH) for _ in seqs_global]
+
+    def my_bin(bins):
+        idx = bins[rank]
+        return [seqs_global[i] for i in idx], [dict(attach_global[i]) for i in idx]
+
+    tm = TreeTimeModel()
+    if world > 1:
+        bins = partition(seqs_global, world, "LB_by_DFS_and_TM", tm, "backward", 2048)
+    else:
+        bins = [list(range(len(seqs_global)))]
+    seqs, attachs = my_bin(bins)
+
+    def build_trie():
+        t = TokenTrie(seqs, [dict(a) for a in attachs])
+        t.backward_permute()
+        return t
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- calibration step (untimed): refit the cost model on this box and re-partition -------------
+    trie = build_trie()
+    layout = linearize_trie(trie, dev)
+    attention.PROFILE = []
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    engine.backward_layout(model, trie, layout, example_loss, 2048)
+    allreduce_gradients(model)
+    torch.cuda.synchronize(dev)
+    t_step = time.perf_counter() - t0
+    t_attn = sum(a.elapsed_time(b) for _, a, b in attention.PROFILE) / 1e3
+    attention.PROFILE = None
+    model.zero_grad(set_to_none=True)
+    if world > 1:
+        st = trie.get_stats("backward", 2048)
+        t_pair = t_attn / max(st["sum_depth"] + st["n_tree_tokens"], 1)
+        t_tok = max(t_step - t_attn, 0.0) / max(st["n_tree_tokens"], 1)
+        coeffs = torch.tensor([t_tok, t_pair], dtype=torch.float64, device=dev)
+        dist.broadcast(coeffs, 0)
+        t_tok, t_pair = coeffs.tolist()
+        import numpy as np
+        tm.coeffs = np.array([0.0, t_tok + t_pair, 0.0, 0.0, t_pair])   # pairs = sum_depth + n_tree_tokens
+        bins = partition(seqs_global, world, "LB_by_DFS_and_TM", tm, "backward", 2048)
+        seqs, attachs = my_bin(bins)
+        trie = build_trie()
+        layout = linearize_trie(trie, dev)
+
+    n_tok_local = layout.n_nodes
+    pairs_local = int(layout.pair_count.item())
+    n_tok_global = int(sum_over_ranks(float(n_tok_local)))
+    seq_tok_global = int(sum_over_ranks(float(trie.n_tokens)))
+    Hq, D, L = cfg.num_attention_heads, cfg.head_dim, cfg.num_hidden_layers
+
+    # ---- device-resident timing --------------------------------------------------------------------
+    def step_resident():
+        loss = engine.backward_layout(model, trie, layout, example_loss, 2048)
+        allreduce_gradients(model)
+        return loss
+
+    for _ in range(args.warmup):
+        step_resident()
+    model.zero_grad(set_to_none=True)
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    attention.PROFILE = []
+    launches0 = _cabi.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else {}
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = _cabi.launch_count - launches0
+    prof = attention.PROFILE
+    attention.PROFILE = None
+    bwd_ms = [a.elapsed_time(b) for k, a, b in prof if k == "bwd"]
+    fwd_ms = [a.elapsed_time(b) for k, a, b in prof if k == "fwd"]
+    ms_per_step = ms_total / args.steps
+    value = n_tok_global / (ms_per_step / 1e3)
+    model.zero_grad(set_to_none=True)
+
+    # ---- end-to-end timing through the public API with host inputs -----------------------------------
+    def step_e2e():
+        t = TokenTrie(seqs, [dict(a) for a in attachs])
+        t.backward_permute()
+        loss = engine.backward(model, t, example_loss, block_size=2048)
+        allreduce_gradients(model)
+        return loss
+
+    step_e2e()
+    model.zero_grad(set_to_none=True)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    sync_all()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    h2d = n_tok_local * 8 + (2 * layout.n_leaf - 1) * 4 + (layout.n_leaf + 1) * 8
+    n_chunks = -(-n_tok_local // engine._chunk_rows(2048))
+    d2h = 4 + 2 * n_chunks * 16
+    model.zero_grad(set_to_none=True)
+
+    # ---- roofline of the dominant kernel (attention backward) ----------------------------------------
+    bwd_flops = pairs_local * Hq * D * 10.0
+    fwd_flops = pairs_local * Hq * D * 4.0
+    bwd_mean = statistics.mean(bwd_ms) if bwd_ms else float("nan")
+    fwd_mean = statistics.mean(fwd_ms) if fwd_ms else float("nan")
+    achieved = bwd_flops / (bwd_mean / 1e3) / 1e12
+    attn_fwd_tflops = fwd_flops / (fwd_mean / 1e3) / 1e12
+    attn_share = (sum(bwd_ms) + sum(fwd_ms)) / max(ev0.elapsed_time(ev1), 1e-9)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(1, 0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": "qwen3-0.6b random-init bf16, one tau2-16k-shaped merged trie per GPU "
+                        "(trunk 6144, fan-out 4x2x2, segments U{1024..3072}, depth<=16384), tree fwd+bwd",
+            "trie_tokens": n_tok_global, "sequence_tokens": seq_tok_global, "unmasked_pairs_rank0": pairs_local,
+            "layers": L, "q_heads": Hq, "kv_heads": cfg.num_key_value_heads, "head_dim": D,
+            "partition": "LB_by_DFS_and_TM" if world > 1 else "single",
+            "inputs_vs_l2": "working set >> 126 MB L2 (no flush needed)",
+            "seq_tokens_per_sec": seq_tok_global / (ms_per_step / 1e3),
+        },
+        "roofline": {
+            "bound": "tensor", "kernel": "tree_attn_bwd_kernel", "achieved": achieved, "peak": peak_tflops,
+            "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None, "peak_source": peak_src,
+            "flops_per_launch": bwd_flops, "ms_per_launch": bwd_mean,
+            "attn_fwd_tflops": attn_fwd_tflops, "attn_fwd_ms_per_launch": fwd_mean,
+            "attn_share_of_step": attn_share,
+        },
+        "cpu_baseline": cpu,
+        "e2e": {"value": n_tok_global / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libdta_b200.so"
-_lib: Optional[C.CDLL] = None
+_lib = None
 
 ABI_VERSION = 1
 TILE = 128
@@ -54,6 +54,7 @@ SIGNATURES = {
     "dta_trie_paths": (_I, [_P, _P, _P, _I, _P, _L, _P, _P, _P]),
     "dta_tile_meta": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dta_tree_attn_fwd": (_I, [_P, _P, _P, _P, _P, C.POINTER(AttnMeta), C.POINTER(AttnShape), _P]),
+    "dta_profile_next_attn": (_I, [_P, _P]),
     "dta_tree_attn_bwd_workspace_bytes": (_Z, [C.POINTER(AttnShape)]),
     "dta_tree_attn_bwd": (_I, [_P] * 9 + [C.POINTER(AttnMeta), C.POINTER(AttnShape), _P, _P]),
     "dta_logprob_row_stats": (_I, [_P, _I, _L, _L, _L, _F, _P, _P]),
@@ -65,11 +66,47 @@ SIGNATURES = {
 }
 
 
+# kernels launched per successful call (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {
+    "dta_lcp_adjacent": 1, "dta_trie_linearize": 2, "dta_trie_paths": 1, "dta_tile_meta": 2,
+    "dta_tree_attn_fwd": 1, "dta_tree_attn_bwd": 3,
+    "dta_logprob_row_stats": 1, "dta_logprob_gather_labels": 1, "dta_logprob_finalize": 1,
+    "dta_logprob_bwd": 1, "dta_logprob_bwd_scatter": 1, "dta_logprob_rowsum_grad": 1,
+}
+launch_count = 0          # kernels of OURS launched by this process so far
+call_count: dict = {}
+
+
+class _Counted:
+    """Callable proxy over one library entry point that keeps the launch tally."""
+    __slots__ = ("fn", "name", "n")
+
+    def __init__(self, fn, name, n):
+        self.fn, self.name, self.n = fn, name, n
+
+    def __call__(self, *args):
+        global launch_count
+        rc = self.fn(*args)
+        if rc == 0:
+            launch_count += self.n
+            call_count[self.name] = call_count.get(self.name, 0) + 1
+        return rc
+
+
+class _Lib:
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name in SIGNATURES:
+            fn = getattr(cdll, name)
+            n = KERNELS_PER_CALL.get(name)
+            setattr(self, name, _Counted(fn, name, n) if n else fn)
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 
 
-def load(build_if_missing: bool = True) -> C.CDLL:
+def load(build_if_missing: bool = True):
     """Load (building first if allowed and needed) the C-ABI library; raise if impossible."""
     global _lib
     if _lib is not None:
@@ -86,8 +123,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn.argtypes = args
     if lib.dta_abi_version() != ABI_VERSION:
         raise DtaError(f"ABI mismatch: library {lib.dta_abi_version()} vs binding {ABI_VERSION}")
-    _lib = lib
-    return lib
+    _lib = _Lib(lib)
+    return _lib
 
 
 def check(rc: int) -> None:

@@ -22,6 +22,21 @@ from .linearize import TrieLayout
 ATTN_NAME = "dta_tree"
 _tls = threading.local()
 
+# bench.py sets this to a list to collect ("fwd"|"bwd", start_event, stop_event) around the MAIN
+# attention kernel of every call (events are recorded inside the C library, on the launch stream).
+PROFILE = None
+
+
+def _arm_profile(lib, kind: str):
+    if PROFILE is None:
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()          # materialise the underlying cudaEvent_t handles
+    b.record()
+    lib.dta_profile_next_attn(a.cuda_event, b.cuda_event)
+    PROFILE.append((kind, a, b))
+
+
 
 def _shape(layout: TrieLayout, q, k, v, o, scale: float) -> _cabi.AttnShape:
     s = _cabi.AttnShape()
@@ -57,6 +72,7 @@ class TreeAttnFunction(torch.autograd.Function):
         lse = torch.empty((q.shape[1], layout.n_pad), dtype=torch.float32, device=q.device)
         shape = _shape(layout, q, k, v, out, scale)
         meta = layout.meta()
+        _arm_profile(lib, "fwd")
         _cabi.check(lib.dta_tree_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
                                           lse.data_ptr(), C.byref(meta), C.byref(shape),
                                           _cabi.stream_ptr(q.device)))
@@ -80,6 +96,7 @@ class TreeAttnFunction(torch.autograd.Function):
             q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         ws = torch.empty(lib.dta_tree_attn_bwd_workspace_bytes(C.byref(shape)), dtype=torch.uint8, device=q.device)
         meta = layout.meta()
+        _arm_profile(lib, "bwd")
         _cabi.check(lib.dta_tree_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
                                           dout.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
                                           dv.data_ptr(), C.byref(meta), C.byref(shape), ws.data_ptr(),

@@ -518,8 +518,11 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
     attr_set = true;
   }
   const int n_tiles = sh->n_pad / DTA_TILE;
+  const ProfileHook hook = take_profile_hook();
+  if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
   tree_attn_bwd_kernel<<<n_tiles * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, p);
   DTA_CHECK_CUDA(cudaGetLastError());
+  if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
 
   {
     const int64_t n_vec = static_cast<int64_t>(sh->n_nodes) * sh->n_q_heads * (kT / 8);

@@ -387,7 +387,10 @@ extern "C" int dta_tree_attn_fwd(const void* q, const void* k, const void* v, vo
     attr_set = true;
   }
   const int grid = p.n_tiles * p.n_kv_heads * p.pairs_per_kv;
+  const ProfileHook hook = take_profile_hook();
+  if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
   tree_attn_fwd_kernel<<<grid, kFwdThreads, smem_bytes, stream>>>(tq, tk, tv, p);
   DTA_CHECK_CUDA(cudaGetLastError());
+  if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
   return DTA_OK;
 }

@@ -18,6 +18,8 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+void arm_profile_hook(void* a, void* b);
+
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -51,6 +53,17 @@ int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int he
   return DTA_OK;
 }
 
+static thread_local ProfileHook g_hook;
+ProfileHook take_profile_hook() {
+  ProfileHook h = g_hook;
+  g_hook = ProfileHook{};
+  return h;
+}
+void arm_profile_hook(void* a, void* b) {
+  g_hook.start = static_cast<cudaEvent_t>(a);
+  g_hook.stop = static_cast<cudaEvent_t>(b);
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -68,5 +81,10 @@ extern "C" {
 const char* dta_last_error(void) { return dta::last_error_buf(); }
 
 int dta_abi_version(void) { return DTA_ABI_VERSION; }
+
+int dta_profile_next_attn(void* start_event, void* stop_event) {
+  dta::arm_profile_hook(start_event, stop_event);
+  return DTA_OK;
+}
 
 }  // extern "C"

@@ -38,4 +38,8 @@ int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int he
 
 int sm_count();
 
+// one-shot profiling events armed by dta_profile_next_attn (thread-local)
+struct ProfileHook { cudaEvent_t start = nullptr, stop = nullptr; };
+ProfileHook take_profile_hook();
+
 }  // namespace dta

@@ -261,6 +261,12 @@ class TreeTrainingEngine:
         if not token_trie.inputs:
             return 0.0
         layout = linearize_trie(token_trie, self.device)
+        return self.backward_layout(model, token_trie, layout, loss_fn, block_size)
+
+    def backward_layout(self, model, token_trie, layout: TrieLayout, loss_fn: Callable,
+                        block_size: Optional[int] = 2048) -> float:
+        """``backward`` for a trie whose HBM layout is already resident (skips the H2D copy and the
+        linearisation kernels; used to time the device-resident hot path)."""
         self.last_layout = layout
         h = self._trunk(model, layout)
         _, W = _decoder_and_head(model)

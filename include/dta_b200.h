@@ -107,6 +107,11 @@ typedef struct {
 int dta_tree_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
                       const dta_attn_meta_t* meta, const dta_attn_shape_t* shape, dta_stream_t stream);
 
+/* Measurement hook (bench.py roofline): the NEXT dta_tree_attn_fwd / dta_tree_attn_bwd call on this
+ * host thread records `start` immediately before and `stop` immediately after its MAIN kernel
+ * (cudaEvent_t handles, on the call's stream), then the hook clears itself.  NULLs disarm it. */
+int dta_profile_next_attn(void* start_event, void* stop_event);
+
 /* Workspace: fp32 dq accumulator [N,Hq,D] + delta [Hq,n_pad]. */
 size_t dta_tree_attn_bwd_workspace_bytes(const dta_attn_shape_t* shape);
 

@@ -1,0 +1,60 @@
+"""The C-ABI library loads and exports every symbol include/dta_b200.h declares (no compute calls)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared():
+    text = (ROOT / "include" / "dta_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dta_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from dynamictreeattn_b200 import _cabi
+    lib = _cabi.load()
+    names = _declared()
+    assert len(names) >= 17
+    raw = ctypes.CDLL(str(_cabi.lib_path()))
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in the header but not exported"
+        assert n in _cabi.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_cabi.SIGNATURES) == names
+    assert lib.dta_abi_version() == _cabi.ABI_VERSION
+    assert lib.dta_trie_workspace_bytes(1000) >= 2 * 11 * 1000 * 4
+
+
+def test_argument_validation_without_gpu():
+    """Invalid sizes are rejected on the host before any launch; the message is retrievable."""
+    from dynamictreeattn_b200 import _cabi
+    lib = _cabi.load()
+    rc = lib.dta_trie_linearize(None, None, 0, 0, 0, None, None, None, None, None, None, None)
+    assert rc != 0
+    assert b"n_leaf" in lib.dta_last_error()
+    rc = lib.dta_logprob_row_stats(None, 7, 1, 1, 1, 1.0, None, None)
+    assert rc != 0 and b"dtype" in lib.dta_last_error()
+
+
+def test_no_cpu_fallback():
+    import torch
+    from dynamictreeattn_b200 import _cabi
+    from dynamictreeattn_b200.attention import tree_attention
+    from dynamictreeattn_b200.linearize import linearize
+    from dynamictreeattn_b200.vocab_parallel import gather_logprobs
+    with pytest.raises(_cabi.DtaError):
+        linearize([torch.tensor([1, 2, 3])], [3], [], "cpu")
+    with pytest.raises(_cabi.DtaError):
+        gather_logprobs(torch.randn(4, 10), torch.zeros(4, dtype=torch.long))
+    with pytest.raises(_cabi.DtaError):
+        q = torch.randn(4, 2, 128).bfloat16()
+        tree_attention(q, q[:, :1], q[:, :1], None)
+
+
+def test_product_never_imports_oracle():
+    pkg = ROOT / "dynamictreeattn_b200"
+    for p in pkg.rglob("*.py"):
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), flags=re.M), p

@@ -1,0 +1,112 @@
+"""Tree-attention kernel micro-benchmark (BASELINE config 5 sweep + the tau2 shape).
+
+    python tools/attn_bench.py [--case tau2|chain|fan|bary|sweep] [--iters 5] [--p TRUNK] [--b FAN]
+
+Times dta_tree_attn_fwd / dta_tree_attn_bwd alone (CUDA events around the main kernels, recorded
+inside the C library) on Hq 16 / Hkv 8 / D 128 bf16 and reports TFLOP/s counting ONLY unmasked
+(q,k) pairs: fwd 4*P*Hq*D, bwd 10*P*Hq*D.  Also the command to put under ncu.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import statistics
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import torch  # noqa: E402
+
+
+def trunk_fan(n_total: int, trunk: int, fan: int, vocab: int = 50000, seed: int = 0):
+    """Family A: shared trunk of `trunk` tokens, then `fan` equal leaves."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randint(0, vocab, (trunk,), generator=g)
+    leaf = (n_total - trunk) // fan
+    firsts = torch.randperm(vocab, generator=g)[:fan]
+    out = []
+    for c in range(fan):
+        s = torch.randint(0, vocab, (leaf,), generator=g)
+        s[0] = firsts[c]
+        out.append(torch.cat([t, s]))
+    return out
+
+
+def bary(n_total: int, fan: int, levels: int, vocab: int = 50000, seed: int = 0):
+    """Family B: fan-out `fan` at each of `levels` levels, equal segments."""
+    n_seg = sum(fan ** l for l in range(levels + 1))
+    seg = max(n_total // n_seg, 1)
+    from trie_cases import synth_trie
+    return synth_trie(seed, seg, tuple([fan] * levels), (seg, seg), vocab=vocab, max_depth=1 << 30)
+
+
+def run_case(name, seqs, iters, Hq=16, Hkv=8, permute="backward"):
+    from dynamictreeattn_b200 import attention
+    from dynamictreeattn_b200.attention import tree_attention
+    from dynamictreeattn_b200.linearize import linearize_trie
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    trie = TokenTrie(seqs)
+    if permute == "backward":
+        trie.backward_permute()
+    elif permute == "forward":
+        trie.forward_permute()
+    lay = linearize_trie(trie, "cuda")
+    N = lay.n_nodes
+    g = torch.Generator(device="cuda").manual_seed(0)
+    q = torch.randn(N, Hq, 128, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    k = torch.randn(N, Hkv, 128, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    v = torch.randn(N, Hkv, 128, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    do = torch.randn(N, Hq, 128, device="cuda", generator=g).bfloat16()
+    P = int(lay.pair_count.item())
+    for _ in range(2):
+        tree_attention(q, k, v, lay).backward(do)
+    attention.PROFILE = []
+    for _ in range(iters):
+        q.grad = k.grad = v.grad = None
+        tree_attention(q, k, v, lay).backward(do)
+    torch.cuda.synchronize()
+    fwd = [a.elapsed_time(b) for kind, a, b in attention.PROFILE if kind == "fwd"]
+    bwd = [a.elapsed_time(b) for kind, a, b in attention.PROFILE if kind == "bwd"]
+    attention.PROFILE = None
+    f, b = statistics.median(fwd), statistics.median(bwd)
+    res = {"case": name, "N": N, "leaves": lay.n_leaf, "pairs": P, "fwd_ms": round(f, 3), "bwd_ms": round(b, 3),
+           "fwd_tflops": round(4 * P * Hq * 128 / f / 1e9, 1), "bwd_tflops": round(10 * P * Hq * 128 / b / 1e9, 1),
+           "fwd_bwd_tflops": round(14 * P * Hq * 128 / (f + b) / 1e9, 1)}
+    print(json.dumps(res), flush=True)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default="tau2")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--p", type=int, default=4096)
+    ap.add_argument("--b", type=int, default=8)
+    ap.add_argument("--n", type=int, default=16384)
+    args = ap.parse_args()
+    if args.case == "tau2":
+        from trie_cases import synth_trie
+        run_case("tau2", synth_trie(0, 6144, (4, 2, 2), (1024, 3072), vocab=151936, max_depth=16384), args.iters)
+    elif args.case == "chain":
+        run_case(f"chain{args.n}", trunk_fan(args.n, 0, 1), args.iters)
+    elif args.case == "fan":
+        run_case(f"fan_p{args.p}_b{args.b}", trunk_fan(args.n, args.p, args.b), args.iters)
+    elif args.case == "bary":
+        import math
+        run_case(f"bary_b{args.b}", bary(args.n, args.b, max(1, math.ceil(math.log(64, args.b)))), args.iters)
+    elif args.case == "sweep":
+        import math
+        for p in (0, 1024, 4096, 8192, 12288):
+            for b in (1, 2, 4, 8, 16, 32, 64):
+                if p == 0 and b > 1:
+                    pass
+                run_case(f"fan_p{p}_b{b}", trunk_fan(args.n, p, b), args.iters)
+        for b in (2, 4, 8, 64):
+            run_case(f"bary_b{b}", bary(args.n, b, max(1, math.ceil(math.log(64, b)))), args.iters)
+
+
+if __name__ == "__main__":
+    main()
