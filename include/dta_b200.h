@@ -103,7 +103,8 @@ typedef struct {
   const int32_t* k_qlast;     /* [n_tiles] */
 } dta_attn_meta_t;
 
-/* out[N,Hq,D] bf16 (o strides), lse[Hq, n_pad] fp32 (natural-log sum-exp of scaled scores). */
+/* out[N,Hq,D] bf16 (o strides), lse[Hq, n_pad] fp32 = log2(sum_k 2^(scale*log2(e)*q.k)), i.e. the
+ * log-sum-exp of the scaled scores in BASE 2 (multiply by ln 2 for the natural-log value). */
 int dta_tree_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
                       const dta_attn_meta_t* meta, const dta_attn_shape_t* shape, dta_stream_t stream);
 
@@ -112,7 +113,7 @@ int dta_tree_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
  * (cudaEvent_t handles, on the call's stream), then the hook clears itself.  NULLs disarm it. */
 int dta_profile_next_attn(void* start_event, void* stop_event);
 
-/* Workspace: fp32 dq accumulator [N,Hq,D] + delta [Hq,n_pad]. */
+/* Workspace: fp32 dq accumulator [N,Hq,D] + delta [Hq,n_pad] + shifted lse [Hq,n_pad]. */
 size_t dta_tree_attn_bwd_workspace_bytes(const dta_attn_shape_t* shape);
 
 /* dout uses the o strides; dq uses the q strides, dk the k strides, dv the v strides. */
