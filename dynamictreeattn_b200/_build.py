@@ -26,6 +26,7 @@ SOURCES = [
     "logprob_kernels.cu",
     "attn_fwd.cu",
     "attn_bwd.cu",
+    "layer_kernels.cu",
 ]
 
 NVCC_FLAGS = [

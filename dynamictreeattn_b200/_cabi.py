@@ -63,6 +63,13 @@ SIGNATURES = {
     "dta_logprob_bwd": (_I, [_P, _I, _L, _L, _L, _F, _P, _P, _P, _P, _P, _L, _P]),
     "dta_logprob_bwd_scatter": (_I, [_P, _I, _L, _L, _F, _P, _P, _P, _L, _L, _P]),
     "dta_logprob_rowsum_grad": (_I, [_P, _P, _L, _P, _P]),
+    "dta_rmsnorm_fwd": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
+    "dta_rmsnorm_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P]),
+    "dta_qknorm_rope_fwd": (_I, [_P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "dta_qknorm_rope_bwd": (_I, [_P, _P, _P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _L, _I, _I, _I,
+                                 _P, _L, _L, _P, _L, _L, _P, _P, _P]),
+    "dta_swiglu_fwd": (_I, [_P, _P, _L, _P, _P]),
+    "dta_swiglu_bwd": (_I, [_P, _P, _P, _L, _P, _P, _P]),
 }
 
 
@@ -72,6 +79,8 @@ KERNELS_PER_CALL = {
     "dta_tree_attn_fwd": 1, "dta_tree_attn_bwd": 3,
     "dta_logprob_row_stats": 1, "dta_logprob_gather_labels": 1, "dta_logprob_finalize": 1,
     "dta_logprob_bwd": 1, "dta_logprob_bwd_scatter": 1, "dta_logprob_rowsum_grad": 1,
+    "dta_rmsnorm_fwd": 1, "dta_rmsnorm_bwd": 1, "dta_qknorm_rope_fwd": 1, "dta_qknorm_rope_bwd": 1,
+    "dta_swiglu_fwd": 1, "dta_swiglu_bwd": 1,
 }
 launch_count = 0          # kernels of OURS launched by this process so far
 call_count: dict = {}

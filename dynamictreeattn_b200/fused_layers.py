@@ -1,0 +1,197 @@
+"""Fused decoder-layer ops around tree attention + a Qwen3 trunk that uses them.
+
+With attention on tcgen05, the ATen elementwise chains of the HF model code (RMSNorm with fp32
+up-casts, q/k-norm, RoPE, SwiGLU, residual adds: ~40 launches per layer, HF
+models/qwen3/modeling_qwen3.py:50-64, 81-83, 137-181, 263-268) cost more than attention itself.
+``fused_trunk_forward`` runs the same decoder arithmetic directly on the model's own parameters with
+five fused sm_100a kernels (csrc/layer_kernels.cu) and cuBLAS GEMMs; gradients land in the same
+``param.grad`` tensors through ordinary autograd.  Models the fused trunk does not cover (biases,
+non-default RoPE, head_dim != 128, sliding-window layers) take the generic HF-plugin path instead.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _cabi
+from .attention import tree_attention
+from .linearize import TrieLayout
+
+__all__ = ["add_rmsnorm", "qknorm_rope", "swiglu", "fused_trunk_forward", "supports_fused_trunk", "rope_table"]
+
+
+def _st(t: torch.Tensor) -> int:
+    return _cabi.stream_ptr(t.device)
+
+
+class _AddRMSNorm(torch.autograd.Function):
+    """(y, s) = (RMSNorm(s) * w, s) with s = x + residual (residual optional)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, residual: Optional[torch.Tensor], weight: torch.Tensor, eps: float):
+        lib = _cabi.load()
+        _cabi.require_cuda(x, weight)
+        x = x.contiguous()
+        n, h = x.shape
+        y = torch.empty_like(x)
+        rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+        if residual is not None:
+            residual = residual.contiguous()
+            s = torch.empty_like(x)
+        else:
+            s = x
+        _cabi.check(lib.dta_rmsnorm_fwd(x.data_ptr(), residual.data_ptr() if residual is not None else None,
+                                        weight.data_ptr(), n, h, eps, y.data_ptr(),
+                                        s.data_ptr() if residual is not None else None, rstd.data_ptr(), _st(x)))
+        ctx.save_for_backward(s, weight, rstd)
+        ctx.has_res = residual is not None
+        if residual is None:
+            return y
+        return y, s
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor, ds: Optional[torch.Tensor] = None):
+        lib = _cabi.load()
+        s, weight, rstd = ctx.saved_tensors
+        n, h = s.shape
+        dy = dy.contiguous()
+        if ds is not None:
+            ds = ds.contiguous()
+        dx = torch.empty_like(s)
+        dw = torch.zeros(h, dtype=torch.float32, device=s.device)
+        _cabi.check(lib.dta_rmsnorm_bwd(dy.data_ptr(), s.data_ptr(), weight.data_ptr(), rstd.data_ptr(),
+                                        ds.data_ptr() if ds is not None else None, n, h, dx.data_ptr(),
+                                        dw.data_ptr(), _st(s)))
+        return dx, (dx if ctx.has_res else None), dw.to(weight.dtype), None
+
+
+def add_rmsnorm(x, residual, weight, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(RMSNorm(x + residual) * weight, x + residual); with ``residual=None`` the sum is ``x`` itself."""
+    if residual is None:
+        return _AddRMSNorm.apply(x, None, weight, eps), x
+    return _AddRMSNorm.apply(x, residual, weight, eps)
+
+
+class _QKNormRope(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, wq, wk, depth, table, eps: float):
+        lib = _cabi.load()
+        n, hq, d = q.shape
+        hkv = k.shape[1]
+        q_out = torch.empty((n, hq, d), dtype=q.dtype, device=q.device)
+        k_out = torch.empty((n, hkv, d), dtype=k.dtype, device=k.device)
+        rstd = torch.empty((n, hq + hkv), dtype=torch.float32, device=q.device)
+        _cabi.check(lib.dta_qknorm_rope_fwd(q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0),
+                                            k.stride(1), wq.data_ptr(), wk.data_ptr(), depth.data_ptr(),
+                                            table.data_ptr(), n, hq, hkv, d, eps, q_out.data_ptr(),
+                                            k_out.data_ptr(), rstd.data_ptr(), _st(q)))
+        ctx.save_for_backward(q, k, wq, wk, depth, table, rstd)
+        return q_out, k_out
+
+    @staticmethod
+    def backward(ctx, dq_out, dk_out):
+        lib = _cabi.load()
+        q, k, wq, wk, depth, table, rstd = ctx.saved_tensors
+        n, hq, d = q.shape
+        hkv = k.shape[1]
+        dq_out, dk_out = dq_out.contiguous(), dk_out.contiguous()
+        dq = torch.empty((n, hq, d), dtype=q.dtype, device=q.device)
+        dk = torch.empty((n, hkv, d), dtype=k.dtype, device=k.device)
+        dwq = torch.zeros(d, dtype=torch.float32, device=q.device)
+        dwk = torch.zeros(d, dtype=torch.float32, device=q.device)
+        _cabi.check(lib.dta_qknorm_rope_bwd(dq_out.data_ptr(), dk_out.data_ptr(), q.data_ptr(), q.stride(0),
+                                            q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), wq.data_ptr(),
+                                            wk.data_ptr(), depth.data_ptr(), table.data_ptr(), rstd.data_ptr(),
+                                            n, hq, hkv, d, dq.data_ptr(), dq.stride(0), dq.stride(1),
+                                            dk.data_ptr(), dk.stride(0), dk.stride(1), dwq.data_ptr(),
+                                            dwk.data_ptr(), _st(q)))
+        return dq, dk, dwq.to(wq.dtype), dwk.to(wk.dtype), None, None, None
+
+
+def qknorm_rope(q, k, wq, wk, depth, table, eps: float):
+    """q [N,Hq,128], k [N,Hkv,128] (strided views ok) -> per-head RMSNorm * w, then RoPE at ``depth``."""
+    return _QKNormRope.apply(q, k, wq, wk, depth, table, eps)
+
+
+class _SwiGLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, up):
+        lib = _cabi.load()
+        gate, up = gate.contiguous(), up.contiguous()
+        out = torch.empty_like(gate)
+        _cabi.check(lib.dta_swiglu_fwd(gate.data_ptr(), up.data_ptr(), gate.numel(), out.data_ptr(), _st(gate)))
+        ctx.save_for_backward(gate, up)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _cabi.load()
+        gate, up = ctx.saved_tensors
+        dout = dout.contiguous()
+        dg, du = torch.empty_like(gate), torch.empty_like(up)
+        _cabi.check(lib.dta_swiglu_bwd(dout.data_ptr(), gate.data_ptr(), up.data_ptr(), gate.numel(), dg.data_ptr(),
+                                       du.data_ptr(), _st(gate)))
+        return dg, du
+
+
+def swiglu(gate, up):
+    return _SwiGLU.apply(gate, up)
+
+
+# ---------------------------------------------------------------------------------------
+# trunk
+# ---------------------------------------------------------------------------------------
+def rope_table(rotary_emb, n_pos: int, device) -> torch.Tensor:
+    """fp32 [n_pos, 128]: cos in [:, :64], sin in [:, 64:], scaled like HF (attention_scaling)."""
+    inv_freq = rotary_emb.inv_freq.to(device=device, dtype=torch.float32)
+    pos = torch.arange(n_pos, device=device, dtype=torch.float32)
+    freqs = pos[:, None] * inv_freq[None, :]
+    scale = float(getattr(rotary_emb, "attention_scaling", 1.0))
+    return torch.cat([freqs.cos() * scale, freqs.sin() * scale], dim=1).contiguous()
+
+
+def supports_fused_trunk(model) -> bool:
+    cfg = model.config
+    base = getattr(model, "model", None)
+    if base is None or getattr(cfg, "model_type", "") != "qwen3" or not hasattr(base, "rotary_emb"):
+        return False
+    hd = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
+    if hd != 128 or cfg.hidden_size % 256 != 0 or cfg.hidden_size > 8192:
+        return False
+    if getattr(cfg, "attention_bias", False) or getattr(cfg, "mlp_bias", False):
+        return False
+    rope = getattr(cfg, "rope_parameters", None) or getattr(cfg, "rope_scaling", None) or {}
+    if isinstance(rope, dict) and rope.get("rope_type", "default") not in ("default", None):
+        return False
+    if any(t != "full_attention" for t in getattr(cfg, "layer_types", []) or []):
+        return False
+    p = next(model.parameters())
+    return p.is_cuda and p.dtype == torch.bfloat16
+
+
+def fused_trunk_forward(model, layout: TrieLayout) -> torch.Tensor:
+    """Last hidden state [N, hidden] (after the final norm) of the linearised trie."""
+    base = model.model
+    cfg = model.config
+    n = layout.n_nodes
+    eps = float(cfg.rms_norm_eps)
+    hq, hkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, 128
+    depth = layout.depth[:n]
+    table = rope_table(base.rotary_emb, max(layout.lens) + 1, layout.tok.device)
+    x = base.embed_tokens(layout.tok)                       # [N, hidden]
+    residual = None
+    for layer in base.layers:
+        at, mlp = layer.self_attn, layer.mlp
+        h, residual = add_rmsnorm(x, residual, layer.input_layernorm.weight, eps)
+        q = F.linear(h, at.q_proj.weight).view(n, hq, d)
+        k = F.linear(h, at.k_proj.weight).view(n, hkv, d)
+        v = F.linear(h, at.v_proj.weight).view(n, hkv, d)
+        q, k = qknorm_rope(q, k, at.q_norm.weight, at.k_norm.weight, depth, table, eps)
+        a = tree_attention(q, k, v, layout, at.scaling)
+        o = F.linear(a.view(n, hq * d), at.o_proj.weight)
+        h, residual = add_rmsnorm(o, residual, layer.post_attention_layernorm.weight, eps)
+        x = F.linear(swiglu(F.linear(h, mlp.gate_proj.weight), F.linear(h, mlp.up_proj.weight)), mlp.down_proj.weight)
+    h, _ = add_rmsnorm(x, residual, base.norm.weight, eps)
+    return h

@@ -26,6 +26,7 @@ import torch
 
 from . import _cabi
 from .attention import use_tree_attention
+from .fused_layers import fused_trunk_forward, supports_fused_trunk
 from .linearize import TrieLayout, linearize_trie
 from .vocab_parallel import logprob_entropy_rows, logprob_entropy_rows_backward
 
@@ -187,6 +188,7 @@ class TreeTrainingEngine:
         self.head_dim = model_config.head_dim if hasattr(model_config, "head_dim") and model_config.head_dim \
             else model_config.hidden_size // model_config.num_attention_heads
         self.head_chunk_rows = 8192
+        self.use_fused_trunk = True      # Qwen3-style bf16 models; others go through the HF attention plugin
         self.last_layout: Optional[TrieLayout] = None
 
     # ---- shared pieces ---------------------------------------------------------------------
@@ -197,6 +199,8 @@ class TreeTrainingEngine:
                 f"Exceeds max_seq_len: cur_len=0, new_tokens={n}, max={self.max_seq_len}")
 
     def _trunk(self, model, layout: TrieLayout) -> torch.Tensor:
+        if self.use_fused_trunk and supports_fused_trunk(model):
+            return fused_trunk_forward(model, layout)           # fused sm_100a layer kernels (N3)
         trunk, _ = _decoder_and_head(model)
         N = layout.n_nodes
         with use_tree_attention(model, layout):

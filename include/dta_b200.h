@@ -164,6 +164,42 @@ int dta_logprob_bwd_scatter(void* dlogits, int dtype, int64_t n_cols, int64_t d_
 int dta_logprob_rowsum_grad(const float* g_lp, const int32_t* row_of, int64_t n_labels, float* g_lp_rowsum,
                             dta_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused layer kernels either side of attention — replace the ATen
+ * elementwise chains of the HF reference model code (HF models/qwen3/modeling_qwen3.py:50-64 RMSNorm,
+ * :81-83 + :137-181 RoPE, :263-268 q/k norm, :81-83 SwiGLU MLP).  bf16 tensors, fp32 math.
+ * ------------------------------------------------------------------------------------- */
+
+/* s = bf16(x + residual) (residual may be NULL: s = x); y = bf16(s * rstd * weight),
+ * rstd[r] = rsqrt(mean(s^2) + eps).  x/residual/y/sum_out: contiguous [n_rows, hidden]. */
+int dta_rmsnorm_fwd(const void* x, const void* residual, const void* weight, int64_t n_rows, int hidden, float eps,
+                    void* y, void* sum_out, float* rstd, dta_stream_t stream);
+
+/* dx = rstd * (g - xh * mean(g * xh)) + dresidual (NULL = 0), g = dy * weight, xh = x * rstd;
+ * dweight[hidden] (fp32) += sum_rows dy * xh.  `x` is the tensor that was normalised (sum_out). */
+int dta_rmsnorm_bwd(const void* dy, const void* x, const void* weight, const float* rstd, const void* dresidual,
+                    int64_t n_rows, int hidden, void* dx, float* dweight, dta_stream_t stream);
+
+/* q_out[n,h,:] = RoPE_{depth[n]}(RMSNorm(q[n,h,:]) * wq), same for k.  q/k: strided [n_rows, H, 128] views
+ * of the projection output; q_out/k_out contiguous; cos_sin[pos][0:64] = cos, [64:128] = sin (fp32);
+ * rstd[n_rows, Hq+Hkv] is saved for the backward. */
+int dta_qknorm_rope_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
+                        int64_t k_row_stride, int64_t k_head_stride, const void* wq, const void* wk,
+                        const int32_t* depth, const float* cos_sin, int64_t n_rows, int n_q_heads, int n_kv_heads,
+                        int head_dim, float eps, void* q_out, void* k_out, float* rstd, dta_stream_t stream);
+
+int dta_qknorm_rope_bwd(const void* dq_out, const void* dk_out, const void* q, int64_t q_row_stride,
+                        int64_t q_head_stride, const void* k, int64_t k_row_stride, int64_t k_head_stride,
+                        const void* wq, const void* wk, const int32_t* depth, const float* cos_sin, const float* rstd,
+                        int64_t n_rows, int n_q_heads, int n_kv_heads, int head_dim, void* dq, int64_t dq_row_stride,
+                        int64_t dq_head_stride, void* dk, int64_t dk_row_stride, int64_t dk_head_stride, float* dwq,
+                        float* dwk, dta_stream_t stream);
+
+/* out = silu(gate) * up;  backward returns d gate and d up. */
+int dta_swiglu_fwd(const void* gate, const void* up, int64_t n_elems, void* out, dta_stream_t stream);
+int dta_swiglu_bwd(const void* dout, const void* gate, const void* up, int64_t n_elems, void* dgate, void* dup,
+                   dta_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

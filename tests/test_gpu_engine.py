@@ -76,3 +76,45 @@ def test_device_linearisation_called_and_launches_counted():
     assert delta["dta_trie_linearize"] == 1 and delta["dta_tile_meta"] == 1
     assert delta["dta_tree_attn_fwd"] == 2 and delta["dta_tree_attn_bwd"] == 2        # one per layer
     assert delta["dta_logprob_row_stats"] >= 1 and delta["dta_logprob_bwd"] >= 1
+
+
+def test_dense_module_matches_oracle_and_tree():
+    """dense.forward/backward (reference dense.py:7-53 signatures) on the GPU vs the fp32 CPU oracle."""
+    from dynamictreeattn_b200 import dense
+    cfg, ref, model = _models()
+    seqs = synth_trie(13, 64, (2, 2), (30, 60), vocab=2048)
+    attachs = [{"w_logprobs": -1.0, "w_entropy": 0.1} for _ in seqs]
+    loss_ref = tree_oracle.dense_backward(ref, seqs, [dict(a) for a in attachs], tree_oracle.example_loss)
+    loss = dense.backward(model, seqs, attachs, tree_oracle.example_loss, act_ckpt=False, use_tqdm=False)
+    assert abs(loss - loss_ref) < 0.02 * abs(loss_ref)
+    r = _ratios(model, ref)
+    assert r[-1] < 1.1e-1 and r[len(r) // 2] < 3e-2
+    lps = dense.forward(model, seqs, use_tqdm=False)
+    lp_ref = tree_oracle.dense_forward(ref, seqs)
+    assert max((a.cpu() - b).abs().max().item() for a, b in zip(lps, lp_ref)) < 0.15
+
+
+def test_fused_trunk_equals_hf_plugin_path():
+    """The fused-layer trunk (N3) and the generic HF-plugin trunk run the same arithmetic: same loss,
+    gradients within bf16 noise of each other and both within tolerance of the fp32 oracle."""
+    from dynamictreeattn_b200.fused_layers import supports_fused_trunk
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    from dynamictreeattn_b200.tree_training_engine import TreeTrainingEngine
+    cfg, ref, model = _models()
+    assert supports_fused_trunk(model)
+    seqs = synth_trie(14, 80, (3, 2), (40, 100), vocab=2048)
+    attachs = [{"w_logprobs": -1.0, "w_entropy": 0.1} for _ in seqs]
+    loss_ref = tree_oracle.dense_backward(ref, seqs, [dict(a) for a in attachs], tree_oracle.example_loss)
+    out = {}
+    for fused in (True, False):
+        model.zero_grad(set_to_none=True)
+        eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 8192)
+        eng.use_fused_trunk = fused
+        trie = TokenTrie(seqs, [dict(a) for a in attachs])
+        trie.backward_permute()
+        loss = eng.backward(model, trie, tree_oracle.example_loss, block_size=2048)
+        r = _ratios(model, ref)
+        assert abs(loss - loss_ref) < 0.02 * abs(loss_ref), (fused, loss, loss_ref)
+        assert r[-1] < 1.1e-1 and r[len(r) // 2] < 3e-2, (fused, r[-1], r[len(r) // 2])
+        out[fused] = (loss, {n: p.grad.float().clone() for n, p in model.named_parameters()})
+    assert abs(out[True][0] - out[False][0]) < 0.01 * abs(loss_ref)

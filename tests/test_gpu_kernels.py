@@ -274,3 +274,82 @@ def test_leaf_order_invariance_full_depth():
         outs[mode] = per_seq
     for sid in outs["forward"]:
         assert _rel(outs["forward"][sid], outs["backward"][sid]) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------
+# fused layer kernels (N3) vs plain torch fp32 references of the same ops
+# ------------------------------------------------------------------------------------------
+def _hf_rmsnorm(x, w, eps):
+    xf = x.float()
+    return xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * w.float()
+
+
+@pytest.mark.parametrize("hidden", [1024, 2048, 256])
+def test_add_rmsnorm_fwd_bwd(hidden):
+    from dynamictreeattn_b200.fused_layers import add_rmsnorm
+    torch.manual_seed(0)
+    n = 777
+    x = torch.randn(n, hidden, device="cuda").bfloat16().requires_grad_(True)
+    r = torch.randn(n, hidden, device="cuda").bfloat16().requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(hidden, device="cuda")).bfloat16().requires_grad_(True)
+    gy = torch.randn(n, hidden, device="cuda").bfloat16()
+    gs = torch.randn(n, hidden, device="cuda").bfloat16()
+    y, s = add_rmsnorm(x, r, w, 1e-6)
+    torch.autograd.backward([y, s], [gy, gs])
+    xr, rr, wr = (t.detach().float().requires_grad_(True) for t in (x, r, w))
+    sr = (xr + rr).detach().bfloat16().float() + ((xr + rr) - (xr + rr).detach())   # value rounded like HF, grad identity
+    yr = _hf_rmsnorm(sr, wr, 1e-6)
+    torch.autograd.backward([yr, sr], [gy.float(), gs.float()])
+    assert _rel(y, yr) < 4e-3 and torch.equal(s.float(), sr.detach())
+    assert _rel(x.grad, xr.grad) < 6e-3 and _rel(r.grad, rr.grad) < 6e-3 and _rel(w.grad, wr.grad) < 6e-3
+    # no residual
+    x2 = x.detach().clone().requires_grad_(True)
+    y2, s2 = add_rmsnorm(x2, None, w.detach(), 1e-6)
+    assert s2 is x2 and _rel(y2, _hf_rmsnorm(x2.detach(), w.detach(), 1e-6)) < 4e-3
+
+
+def test_qknorm_rope_fwd_bwd():
+    from dynamictreeattn_b200.fused_layers import qknorm_rope
+    torch.manual_seed(0)
+    n, hq, hkv, d = 500, 4, 2, 128
+    buf = torch.randn(n, (hq + hkv) * d, device="cuda").bfloat16().requires_grad_(True)
+    wq = (1 + 0.1 * torch.randn(d, device="cuda")).bfloat16().requires_grad_(True)
+    wk = (1 + 0.1 * torch.randn(d, device="cuda")).bfloat16().requires_grad_(True)
+    depth = torch.randint(0, 9000, (n,), device="cuda", dtype=torch.int32)
+    inv_freq = 1.0 / (1e6 ** (torch.arange(0, d, 2, device="cuda").float() / d))
+    pos = torch.arange(9000, device="cuda").float()
+    fr = pos[:, None] * inv_freq[None]
+    table = torch.cat([fr.cos(), fr.sin()], 1).contiguous()
+    q = buf[:, :hq * d].view(n, hq, d)
+    k = buf[:, hq * d:].view(n, hkv, d)
+    qo, ko = qknorm_rope(q, k, wq, wk, depth, table, 1e-6)
+    gq, gk = torch.randn_like(qo), torch.randn_like(ko)
+    torch.autograd.backward([qo, ko], [gq, gk])
+
+    def ref(xr, w):
+        xh = _hf_rmsnorm(xr, w, 1e-6)
+        cos = torch.cat([fr.cos(), fr.cos()], 1)[depth.long()][:, None, :]
+        sin = torch.cat([fr.sin(), fr.sin()], 1)[depth.long()][:, None, :]
+        rot = torch.cat([-xh[..., d // 2:], xh[..., :d // 2]], -1)
+        return xh * cos + rot * sin
+    bufr = buf.detach().float().requires_grad_(True)
+    wqr, wkr = wq.detach().float().requires_grad_(True), wk.detach().float().requires_grad_(True)
+    qr = ref(bufr[:, :hq * d].view(n, hq, d), wqr)
+    kr = ref(bufr[:, hq * d:].view(n, hkv, d), wkr)
+    torch.autograd.backward([qr, kr], [gq.float(), gk.float()])
+    assert _rel(qo, qr) < 4e-3 and _rel(ko, kr) < 4e-3
+    assert _rel(buf.grad, bufr.grad) < 6e-3 and _rel(wq.grad, wqr.grad) < 6e-3 and _rel(wk.grad, wkr.grad) < 6e-3
+
+
+def test_swiglu_fwd_bwd():
+    from dynamictreeattn_b200.fused_layers import swiglu
+    torch.manual_seed(0)
+    g = (2 * torch.randn(333, 3072, device="cuda")).bfloat16().requires_grad_(True)
+    u = torch.randn(333, 3072, device="cuda").bfloat16().requires_grad_(True)
+    go = torch.randn(333, 3072, device="cuda").bfloat16()
+    m = swiglu(g, u)
+    m.backward(go)
+    gr, ur = g.detach().float().requires_grad_(True), u.detach().float().requires_grad_(True)
+    mr = torch.nn.functional.silu(gr) * ur
+    mr.backward(go.float())
+    assert _rel(m, mr) < 4e-3 and _rel(g.grad, gr.grad) < 6e-3 and _rel(u.grad, ur.grad) < 6e-3
