@@ -42,14 +42,20 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(int mode, int iters, long
         if (m == 1) umma_ss_lo(d, ka + ko, nb + no, i_kn, kk > 0);
         if (m == 2) umma_ts_lo(d, ta + kk * 8, nb + no, i_kn, kk > 0);
         if (m == 3) umma_ss_lo(d, na + no, nb + no, i_nn, kk > 0);
+        if (m == 5) umma_ss_lo(d, ka + ko, kb + ko, make_idesc_bf16(T, 64, false, false), kk > 0);   // N = 64
+        if (m == 6) umma_ss_lo(d, ka + ko, kb + ko, make_idesc_bf16(T, 256, false, false), kk > 0);  // N = 256
       }
     };
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       if (mode < 4) {
         gemm(mode, tmem + (it & 1) * 128);
-      } else {
+      } else if (mode == 4) {
         gemm(0, tmem); gemm(0, tmem + 128); gemm(2, tmem + 256); gemm(3, tmem + 128); gemm(1, tmem + 256);
+      } else if (mode == 5) {
+        gemm(5, tmem); gemm(5, tmem + 64); gemm(5, tmem + 128); gemm(5, tmem + 192); gemm(5, tmem + 256);
+      } else {
+        gemm(6, tmem); gemm(6, tmem + 256); gemm(6, tmem); gemm(6, tmem + 256); gemm(6, tmem);
       }
     }
     umma_commit(bar);
@@ -73,7 +79,7 @@ int main() {
   cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 4000;
   for (int grid : {1, sms}) {
-    for (int mode = 0; mode < 5; ++mode) {
+    for (int mode = 4; mode < 7; ++mode) {
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       bench_kernel<<<grid, 128, smem>>>(mode, 200, d_cycles);
@@ -89,7 +95,7 @@ int main() {
       long long mx = 0;
       for (auto c : h) mx = c > mx ? c : mx;
       const double n_mma = static_cast<double>(iters) * (mode < 4 ? 8 : 40);
-      const double flops = n_mma * 2.0 * T * T * 16 * grid;
+      const double flops = n_mma * 2.0 * T * (mode == 5 ? 64 : mode == 6 ? 256 : T) * 16 * grid;
       printf("umma_bench grid=%d mode=%d: %.1f cycles/MMA (max over CTAs), %.3f ms, %.0f TFLOP/s, eff. clock %.0f MHz\n",
              grid, mode, mx / n_mma, ms, flops / (ms * 1e-3) / 1e12, mx / (ms * 1e-3) / 1e6);
     }
