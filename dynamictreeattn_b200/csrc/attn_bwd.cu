@@ -39,6 +39,7 @@ static constexpr int kTile = 2 * kHalf;              // 32 KB
 static constexpr int kBwdThreads = 512;
 static constexpr int kProducerWarp = 14, kMmaWarp = 15;
 static constexpr float kLog2e = 1.4426950408889634f;
+static constexpr int kDefaultBwdPoly = 2;            // of every 8 exponentials, on the FMA pipes
 
 struct BwdSmem {
   static constexpr int k = 0;
@@ -81,6 +82,8 @@ __device__ __forceinline__ void red_add_f32(float* addr, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 
+// kPolyOf8: how many of every 8 exponentials of the P^T pass run on the FMA pipes (poly_exp2)
+template <int kPolyOf8>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -331,10 +334,13 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int c4 = 0; c4 < 16; ++c4) {
           const float4 l4 = reinterpret_cast<const float4*>(lse)[c4];
-          pr[c4 * 4 + 0] = fast_exp2(fmaf(pr[c4 * 4 + 0], p.scale_log2, l4.x));
-          pr[c4 * 4 + 1] = fast_exp2(fmaf(pr[c4 * 4 + 1], p.scale_log2, l4.y));
-          pr[c4 * 4 + 2] = fast_exp2(fmaf(pr[c4 * 4 + 2], p.scale_log2, l4.z));
-          pr[c4 * 4 + 3] = fast_exp2(fmaf(pr[c4 * 4 + 3], p.scale_log2, l4.w));
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c4 * 4 + u;
+            const float x = fmaf(pr[c], p.scale_log2, lv[u]);
+            pr[c] = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
+          }
         }
       } else {
 #pragma unroll
@@ -344,7 +350,8 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int c = c4 * 4 + u;
-            const float v = fast_exp2(fmaf(pr[c], p.scale_log2, lv[u]));
+            const float x = fmaf(pr[c], p.scale_log2, lv[u]);
+            const float v = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
             pr[c] = (c >= vis_lo && c < vis_hi) ? v : 0.f;
           }
         }
@@ -623,15 +630,20 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   p.debug_flags = getenv("DTA_DEBUG_FLAGS") ? atoi(getenv("DTA_DEBUG_FLAGS")) : 0;
   p.trace = g_bwd_trace;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    DTA_CHECK_CUDA(cudaFuncSetAttribute(tree_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::total));
-    attr_set = true;
+  using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const BwdParams);
+  static Kernel kernel = nullptr;
+  if (!kernel) {
+    // share of the exponentials computed on the FMA pipes; DTA_BWD_POLY (0..4 of every 8) is a tuning knob
+    const char* e = getenv("DTA_BWD_POLY");
+    const int poly = e ? atoi(e) : kDefaultBwdPoly;
+    kernel = poly <= 0 ? tree_attn_bwd_kernel<0> : poly == 1 ? tree_attn_bwd_kernel<1>
+           : poly == 2 ? tree_attn_bwd_kernel<2> : poly == 3 ? tree_attn_bwd_kernel<3> : tree_attn_bwd_kernel<4>;
+    DTA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::total));
   }
   const int n_tiles = sh->n_pad / DTA_TILE;
   const ProfileHook hook = take_profile_hook();
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
-  tree_attn_bwd_kernel<<<n_tiles * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, p);
+  kernel<<<n_tiles * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
 

@@ -24,6 +24,7 @@
 #include "dta_common.cuh"
 #include "dta_ptx.cuh"
 #include "../../include/dta_b200.h"
+#include <cstdlib>
 
 namespace dta {
 
@@ -39,6 +40,7 @@ static constexpr int kMaxLive = 4096;
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kLn2 = 0.6931471805599453f;
 static constexpr float kRescaleThreshold = 8.0f;      // log2 units
+static constexpr int kDefaultFwdPoly = 2;             // of every 8 exponentials, on the FMA pipes
 
 struct FwdSmem {
   // offsets inside the 1024-aligned dynamic shared buffer
@@ -65,6 +67,8 @@ struct FwdParams {
   float scale_log2;
 };
 
+// kPolyOf8: how many of every 8 exponentials run on the FMA pipes (poly_exp2) instead of MUFU
+template <int kPolyOf8>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const FwdParams p) {
@@ -302,8 +306,10 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = fast_exp2(fmaf(s[c * 32 + i], p.scale_log2, -mref));
-            const float p1 = fast_exp2(fmaf(s[c * 32 + i + 1], p.scale_log2, -mref));
+            const float x0 = fmaf(s[c * 32 + i], p.scale_log2, -mref);
+            const float x1 = fmaf(s[c * 32 + i + 1], p.scale_log2, -mref);
+            const float p0 = exp2_slot_on_fma<kPolyOf8>(i) ? poly_exp2(x0) : fast_exp2(x0);
+            const float p1 = exp2_slot_on_fma<kPolyOf8>(i + 1) ? poly_exp2(x1) : fast_exp2(x1);
             lsum += p0 + p1;
             pk[i >> 1] = pack_bf16x2(p0, p1);
           }
@@ -397,15 +403,20 @@ extern "C" int dta_tree_attn_fwd(const void* q, const void* k, const void* v, vo
   p.scale_log2 = sh->scale * kLog2e;
 
   const int smem_bytes = FwdSmem::total + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DTA_CHECK_CUDA(cudaFuncSetAttribute(tree_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
+  using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);
+  static Kernel kernel = nullptr;
+  if (!kernel) {
+    // share of the exponentials computed on the FMA pipes; DTA_FWD_POLY (0..4 of every 8) is a tuning knob
+    const char* e = getenv("DTA_FWD_POLY");
+    const int poly = e ? atoi(e) : kDefaultFwdPoly;
+    kernel = poly <= 0 ? tree_attn_fwd_kernel<0> : poly == 1 ? tree_attn_fwd_kernel<1>
+           : poly == 2 ? tree_attn_fwd_kernel<2> : poly == 3 ? tree_attn_fwd_kernel<3> : tree_attn_fwd_kernel<4>;
+    DTA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
   const int grid = p.n_tiles * p.n_kv_heads * p.pairs_per_kv;
   const ProfileHook hook = take_profile_hook();
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
-  tree_attn_fwd_kernel<<<grid, kFwdThreads, smem_bytes, stream>>>(tq, tk, tv, p);
+  kernel<<<grid, kFwdThreads, smem_bytes, stream>>>(tq, tk, tv, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
   return DTA_OK;

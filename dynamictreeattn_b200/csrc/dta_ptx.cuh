@@ -276,6 +276,28 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes: floor by a round-down add of 1.5*2^23, degree-3 minimax polynomial on the
+// fraction in [0,1), exponent patched in with an integer shift-add.  Relative error < 1e-4 (far below
+// bf16 rounding of the probabilities it feeds).  MUFU does only 16 ex2 per clock per SM, which makes a
+// 128x128 softmax tile cost as many cycles as its two MMAs; moving a fixed fraction of the exponentials
+// here balances the two pipes.  x is clamped at -126 (result ~1e-38 instead of 0).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  float fl;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(fl) : "f"(x), "f"(12582912.f));
+  const float f = x - (fl - 12582912.f);
+  float p = fmaf(f, 0.077119089663f, 0.227564394474f);
+  p = fmaf(p, f, 0.695146143436f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(fl) << 23));
+}
+
+// Compile-time spreading of kOf8 FMA-pipe slots over every 8 consecutive exponentials (Bresenham).
+template <int kOf8>
+__device__ __forceinline__ constexpr bool exp2_slot_on_fma(int e) {
+  return ((e & 7) * kOf8) / 8 != (((e & 7) + 1) * kOf8) / 8;
+}
+
 // 128-byte swizzle: byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a [rows][128 B] tile
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
   return row * 128u + ((chunk ^ (row & 7u)) << 4);

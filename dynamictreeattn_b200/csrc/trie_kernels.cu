@@ -6,6 +6,7 @@
 // tree_training_engine.py:541-546, 588-594).  These kernels are HBM/latency-bound integer
 // work: coalesced grid-stride loops, warp-shuffle scans, no tensor cores.
 #include "dta_common.cuh"
+#include <cstdlib>
 #include "../../include/dta_b200.h"
 
 namespace dta {
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const int32_t* __restr
                                                           int32_t* __restrict__ q_order,
                                                           int32_t* __restrict__ q_nlive,
                                                           int32_t* __restrict__ k_order,
-                                                          int32_t* __restrict__ k_qlast) {
+                                                          int32_t* __restrict__ k_qlast, int k_bucket) {
   for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
     const int q0 = i * DTA_TILE;
     int live = 0;
@@ -261,10 +262,10 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const int32_t* __restr
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
-    const int wq = q_nlive[i], wk = k_qlast[i] - i;
+    const int wq = q_nlive[i], wk = (k_qlast[i] - i) / k_bucket;
     int rq = 0, rk = 0;
     for (int j = 0; j < n_tiles; ++j) {
-      const int oq = q_nlive[j], ok = k_qlast[j] - j;
+      const int oq = q_nlive[j], ok = (k_qlast[j] - j) / k_bucket;
       rq += (oq > wq || (oq == wq && j < i)) ? 1 : 0;
       rk += (ok > wk || (ok == wk && j < i)) ? 1 : 0;
     }
@@ -351,7 +352,9 @@ int dta_tile_meta(const int32_t* subtree_end, const int32_t* depth, int n_nodes,
   tile_minmax_kernel<<<(n_tiles * 32 + 255) / 256, 256, 0, stream>>>(
       subtree_end, depth, n_nodes, n_tiles, kmax_end, kmin_end, reinterpret_cast<unsigned long long*>(pair_count));
   DTA_CHECK_CUDA(cudaGetLastError());
-  tile_order_kernel<<<1, 1024, 0, stream>>>(kmax_end, n_tiles, q_order, q_nlive, k_order, k_qlast);
+  const char* kb = getenv("DTA_K_ORDER_BUCKET");      // experiment: coarser weight classes keep DFS neighbours together
+  const int k_bucket = kb && atoi(kb) > 0 ? atoi(kb) : 1;
+  tile_order_kernel<<<1, 1024, 0, stream>>>(kmax_end, n_tiles, q_order, q_nlive, k_order, k_qlast, k_bucket);
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
 }

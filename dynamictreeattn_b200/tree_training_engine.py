@@ -123,7 +123,12 @@ class _TreeHeadLoss(torch.autograd.Function):
         N = layout.n_nodes
         h = hidden.detach()
         W = weight.detach()
-        lp_nodes, ent_nodes, logz, plan = engine._head_forward(h, W, layout, chunk_rows)
+        need_h = hidden.requires_grad
+        need_w = weight.requires_grad
+        # With HBM to spare (180 GB on B200) the bf16 logits chunks stay resident between the statistics
+        # pass and the gradient pass, which saves re-running the [rows, hidden] x [hidden, vocab] GEMM.
+        keep = (need_h or need_w) and engine._can_keep_logits(N, W.shape[0], h.element_size(), h.device)
+        lp_nodes, ent_nodes, logz, plan, kept = engine._head_forward(h, W, layout, chunk_rows, keep_logits=keep)
 
         # ---- user loss on per-node vectors (tiny autograd graph) --------------------------
         with torch.enable_grad():
@@ -141,17 +146,18 @@ class _TreeHeadLoss(torch.autograd.Function):
         loss = total.detach()
 
         # ---- head backward, chunked -------------------------------------------------------
-        need_h = hidden.requires_grad
-        need_w = weight.requires_grad
         dh = torch.empty_like(h) if need_h else None
         dW32 = torch.zeros(W.shape, dtype=torch.float32, device=W.device) if need_w else None
         if need_h or need_w:
             g_lp = torch.zeros_like(lp_nodes) if g_lp is None else g_lp.float()
             g_ent = torch.zeros_like(ent_nodes) if g_ent is None else g_ent.float()
-            for a in range(0, N, chunk_rows):
+            for ci, a in enumerate(range(0, N, chunk_rows)):
                 b = min(a + chunk_rows, N)
                 e0, e1 = plan.span(a, b)
-                logits = h[a:b] @ W.t()
+                if kept is not None:
+                    logits, kept[ci] = kept[ci], None
+                else:
+                    logits = h[a:b] @ W.t()
                 row_of = (plan.row[e0:e1] - a).to(torch.int32)
                 logprob_entropy_rows_backward(logits, plan.label[e0:e1], row_of, 1.0, 0, logz[a:b], ent_nodes[a:b],
                                               g_lp[plan.child[e0:e1]], g_ent[a:b], out=logits)
@@ -188,6 +194,7 @@ class TreeTrainingEngine:
         self.head_dim = model_config.head_dim if hasattr(model_config, "head_dim") and model_config.head_dim \
             else model_config.hidden_size // model_config.num_attention_heads
         self.head_chunk_rows = 8192
+        self.keep_head_logits = True     # keep bf16 logits between the head's two passes when HBM allows
         self.use_fused_trunk = True      # Qwen3-style bf16 models; others go through the HF attention plugin
         self.last_layout: Optional[TrieLayout] = None
 
@@ -209,14 +216,25 @@ class TreeTrainingEngine:
                         use_cache=False)
         return out.last_hidden_state[0]                       # [N, hidden]
 
-    def _head_forward(self, h: torch.Tensor, W: torch.Tensor, layout: TrieLayout, chunk_rows: int):
-        """Per-node log-prob of the edge INTO the node (roots: 0) and per-node entropy."""
+    def _can_keep_logits(self, n_rows: int, vocab: int, elem: int, dev) -> bool:
+        """True when all logits chunks of one step fit in free HBM with a 24 GB margin."""
+        if not self.keep_head_logits:
+            return False
+        free, _ = torch.cuda.mem_get_info(dev)
+        free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+        return n_rows * vocab * elem + (24 << 30) < free
+
+    def _head_forward(self, h: torch.Tensor, W: torch.Tensor, layout: TrieLayout, chunk_rows: int,
+                      keep_logits: bool = False):
+        """Per-node log-prob of the edge INTO the node (roots: 0) and per-node entropy
+        (+ the logits chunks themselves when ``keep_logits``)."""
         N = layout.n_nodes
         dev = h.device
         plan = _EdgePlan(layout)
         lp_nodes = torch.zeros(N, dtype=torch.float32, device=dev)
         ent_nodes = torch.empty(N, dtype=torch.float32, device=dev)
         logz = torch.empty(N, dtype=torch.float32, device=dev)
+        kept = [] if keep_logits else None
         for a in range(0, N, chunk_rows):
             b = min(a + chunk_rows, N)
             e0, e1 = plan.span(a, b)
@@ -226,8 +244,10 @@ class TreeTrainingEngine:
             lp_nodes[plan.child[e0:e1]] = x_label - lz[row_of.long()]
             ent_nodes[a:b] = ent
             logz[a:b] = lz
+            if kept is not None:
+                kept.append(logits)
             del logits
-        return lp_nodes, ent_nodes, logz, plan
+        return lp_nodes, ent_nodes, logz, plan, kept
 
     def _chunk_rows(self, block_size: Optional[int]) -> int:
         rows = self.head_chunk_rows
@@ -249,7 +269,7 @@ class TreeTrainingEngine:
         self.last_layout = layout
         h = self._trunk(model, layout)
         _, W = _decoder_and_head(model)
-        lp_nodes, _, _, _ = self._head_forward(h, W, layout, self.head_chunk_rows)
+        lp_nodes, _, _, _, _ = self._head_forward(h, W, layout, self.head_chunk_rows)
         for i, attach_list in enumerate(token_trie.attach_lists):
             for attach, length in attach_list:
                 path = layout.path_of_leaf(i, length).long()

@@ -79,7 +79,7 @@ int main() {
   cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 4000;
   for (int grid : {1, sms}) {
-    for (int mode = 4; mode < 7; ++mode) {
+    for (int mode = 0; mode < 7; ++mode) {
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       bench_kernel<<<grid, 128, smem>>>(mode, 200, d_cycles);
