@@ -38,27 +38,38 @@ static constexpr int kHalf = kT * 128;               // [128 rows][64 bf16] swiz
 static constexpr int kTile = 2 * kHalf;              // 32 KB
 static constexpr int kBwdThreads = 512;
 static constexpr int kProducerWarp = 14, kMmaWarp = 15;
+static constexpr int kQStages = 2;                   // Q ring depth
+static constexpr int kDqRows = 16;                   // query rows per dQ reduce box (2 KB per warp and buffer)
+static constexpr int kAug = kT * 16;                 // one un-swizzled [128][8 bf16] K-chunk, bytes
 static constexpr float kLog2e = 1.4426950408889634f;
-static constexpr int kDefaultBwdPoly = 2;            // of every 8 exponentials, on the FMA pipes
+static constexpr bool kDefaultDqTma = true;
+static constexpr int kDefaultL2Ahead = 0;
+static constexpr int kDefaultRedGap = 0;             // see the drain warps
+static constexpr int kDefaultBwdPoly = 0;            // of every 8 exponentials, on the FMA pipes
 
 struct BwdSmem {
   static constexpr int k = 0;
   static constexpr int v = k + kTile;
-  static constexpr int q = v + kTile;                 // 2 stages
-  static constexpr int d_o = q + 2 * kTile;           // 2 stages
-  static constexpr int ds = d_o + 2 * kTile;
-  static constexpr int lse = ds + kTile;              // float[2][128]
-  static constexpr int delta = lse + 2 * kT * 4;      // float[2][128]
-  static constexpr int bars = delta + 2 * kT * 4;
-  static constexpr int n_bars = 1 + 8 + 8;
+  static constexpr int q = v + kTile;                 // kQStages stages
+  static constexpr int d_o = q + kQStages * kTile;    // ONE stage (see the ring note in the kernel)
+  static constexpr int ds = d_o + kTile;
+  // un-swizzled K-major [128 rows][8 bf16] chunks (2 KB each) for the broadcast k-step (see kernel header)
+  static constexpr int aug_q = ds + kTile;            // kQStages chunks: per-query (lse hi, mid, lo, 0...)
+  static constexpr int aug_do = aug_q + kQStages * kAug;   // 1 chunk: per-query -(delta hi, mid, lo, 0...)
+  static constexpr int aug_one = aug_do + kAug;       // 1 chunk: (1, 1, 1, 0...) in every row
+  static constexpr int aug_zero = aug_one + kAug;     // 1 chunk of zeros = k columns 8..15 of all of the above
+  // dQ staging for the bulk tensor reduce: per drain warp two [kDqRows queries][32 floats] buffers
+  static constexpr int dq_stage = aug_zero + kAug;
+  static constexpr int bars = dq_stage + 4 * 2 * kDqRows * 128;
+  static constexpr int n_bars = 1 + 2 * kQStages + 2 + 8;
   static constexpr int misc = bars + n_bars * 8;
   static constexpr int total = misc + 16;
 };
 static_assert(BwdSmem::total <= 232448, "backward kernel shared memory exceeds 227 KB");
 
 struct BwdParams {
-  const float* lse;        // [Hq, n_pad]  log2(scale) - lse2  (written by the delta pre-pass)
-  const float* delta;      // [Hq, n_pad]
+  const __nv_bfloat16* aug_lse;    // [Hq, n_pad, 8]  3-term bf16 split of (log2(scale) - lse2) / scale_log2, then zeros
+  const __nv_bfloat16* aug_delta;  // [Hq, n_pad, 8]  3-term bf16 split of -delta, then zeros   (both: delta pre-pass)
   float* dq_accum;         // [n_pad, Hq, 128] fp32
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
@@ -69,47 +80,53 @@ struct BwdParams {
   int n_nodes, n_pad, n_q_heads, n_kv_heads, group;
   int64_t k_row_stride, k_head_stride, v_row_stride, v_head_stride;
   float scale, scale_log2, inv_scale;
-  int debug_flags;         // bit 0: skip the dQ reds (timing experiments only)
+  int l2_ahead;            // L2 prefetch distance of the Q / dO tiles, in steps (0 = off)
+  int red_gap;             // dependent integer ops between two dQ reds of a drain warp (issue pacing)
+  int debug_flags;         // timing ablations / trace modes (see the uses); 0 in production
   long long* trace;        // debug timeline (NULL in production): [step][16] clock64 stamps of CTA 0
 };
 
 #define DTA_TRACE(ev)                                                                         \
   do {                                                                                        \
-    if (p.trace != nullptr && blockIdx.x == 0 && it < 48) p.trace[it * 16 + (ev)] = clock64(); \
+    if (p.trace != nullptr && blockIdx.x == 0 && it < 48)                                     \
+      p.trace[it * 16 + (ev)] = clock64();                                                    \
   } while (0)
-
+// trace mode 2 (debug flag 32): per compute warp, slot w = P^T pass done, slot 8 + w = dS^T pass done
 __device__ __forceinline__ void red_add_f32(float* addr, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 
 // kPolyOf8: how many of every 8 exponentials of the P^T pass run on the FMA pipes (poly_exp2)
-template <int kPolyOf8>
+// kDqTma: dQ tiles leave through shared memory + cp.reduce.async.bulk.tensor (TMA) instead of per-lane reds
+template <int kPolyOf8, bool kDqTma>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                     const BwdParams p) {
+                     const __grid_constant__ CUtensorMap tmap_dq, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem + BwdSmem::k;
   uint8_t* sV = smem + BwdSmem::v;
   uint8_t* sQ = smem + BwdSmem::q;
   uint8_t* sdO = smem + BwdSmem::d_o;
   uint8_t* sdS = smem + BwdSmem::ds;
-  float* sLse = reinterpret_cast<float*>(smem + BwdSmem::lse);
-  float* sDelta = reinterpret_cast<float*>(smem + BwdSmem::delta);
+  uint8_t* sAugQ = smem + BwdSmem::aug_q;
+  uint8_t* sAugDO = smem + BwdSmem::aug_do;
+  uint8_t* sAugOne = smem + BwdSmem::aug_one;
+  uint8_t* sAugZero = smem + BwdSmem::aug_zero;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::bars);
   uint64_t* bar_kv_full = bars;
-  uint64_t* bar_q_full = bars + 1;      // [2]
-  uint64_t* bar_q_empty = bars + 3;     // [2]
-  uint64_t* bar_do_full = bars + 5;     // [2]
-  uint64_t* bar_do_empty = bars + 7;    // [2]
-  uint64_t* bar_st_full = bars + 9;     // S^T ready
-  uint64_t* bar_p_full = bars + 10;     // P^T written (256 arrivals)
-  uint64_t* bar_dp_full = bars + 11;    // dP^T ready
-  uint64_t* bar_ds_full = bars + 12;    // dS^T in smem (256 arrivals)
-  uint64_t* bar_ds_empty = bars + 13;   // dK/dQ MMAs of the step done -> sdS reusable
-  uint64_t* bar_dq_full = bars + 14;    // dQ tile ready in R1
-  uint64_t* bar_r1_free = bars + 15;    // dQ tile copied out of R1 (128 arrivals)
-  uint64_t* bar_dkv_full = bars + 16;   // everything done
+  uint64_t* bar_q_full = bars + 1;                    // [kQStages]
+  uint64_t* bar_q_empty = bar_q_full + kQStages;      // [kQStages]
+  uint64_t* bar_do_full = bar_q_empty + kQStages;     // single dO stage, one phase per step
+  uint64_t* bar_do_empty = bar_do_full + 1;
+  uint64_t* bar_st_full = bar_do_empty + 1;           // S^T ready
+  uint64_t* bar_p_full = bar_st_full + 1;             // P^T written (8 warp arrivals)
+  uint64_t* bar_dp_full = bar_p_full + 1;             // dP^T ready
+  uint64_t* bar_ds_full = bar_dp_full + 1;            // dS^T in smem (8 warp arrivals)
+  uint64_t* bar_ds_empty = bar_ds_full + 1;           // dK/dQ MMAs of the step done -> sdS reusable
+  uint64_t* bar_dq_full = bar_ds_empty + 1;           // dQ tile ready in R1
+  uint64_t* bar_r1_free = bar_dq_full + 1;            // dQ tile copied out of R1 (4 warp arrivals)
+  uint64_t* bar_dkv_full = bar_r1_free + 1;           // everything done
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + BwdSmem::misc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,16 +147,24 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_do);
+    if (kDqTma) tma_prefetch_desc(&tmap_dq);
+  }
+  if (warp < 4) {
+    // constant operands of the broadcast k-step: ones (three of them, matching the 3-term splits) and zeros
+    const int r = threadIdx.x;
+    *reinterpret_cast<uint4*>(sAugOne + r * 16) = make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sAugZero + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
   }
   if (warp == kMmaWarp) {
     if (lane == 0) {
       mbar_init(bar_kv_full, 1);
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < kQStages; ++s) {
         mbar_init(bar_q_full + s, 1);
         mbar_init(bar_q_empty + s, 1);
-        mbar_init(bar_do_full + s, 1);
-        mbar_init(bar_do_empty + s, 1);
       }
+      mbar_init(bar_do_full, 1);
+      mbar_init(bar_do_empty, 1);
       mbar_init(bar_st_full, 1);
       mbar_init(bar_p_full, 8);
       mbar_init(bar_dp_full, 1);
@@ -168,24 +193,30 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tma_load_3d(sK + h * kHalf, &tmap_k, bar_kv_full, h * 64, kvh, k0);
         tma_load_3d(sV + h * kHalf, &tmap_v, bar_kv_full, h * 64, kvh, k0);
       }
+      // Ring shape.  Q(it) is read by the first MMA of a step (S^T) and by the last (dK): two stages.  dO(it) is
+      // read by dP^T(it) and dV(it) only -- both early -- and dO(it+1) is not needed before dP^T(it+1), the LAST
+      // MMA of step it: one stage, reloaded as soon as dV(it) retires, has a whole step of slack.
       for (int it = 0; it < n_iter; ++it) {
         const int head = kvh * p.group + it / n_qt;
         const int q0 = (jt + it % n_qt) * kT;
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+        const int st = it % kQStages;
+        const uint32_t ph = (it / kQStages) & 1;
         mbar_wait(bar_q_empty + st, ph ^ 1);
-        mbar_arrive_expect_tx(bar_q_full + st, kTile + kT * 4);
+        const int64_t aug_off = (static_cast<int64_t>(head) * p.n_pad + q0) * 8;
+        mbar_arrive_expect_tx(bar_q_full + st, kTile + kAug);
         for (int h = 0; h < 2; ++h) tma_load_3d(sQ + st * kTile + h * kHalf, &tmap_q, bar_q_full + st, h * 64, head, q0);
-        bulk_load_1d(sLse + st * kT, p.lse + static_cast<int64_t>(head) * p.n_pad + q0, kT * 4, bar_q_full + st);
-        mbar_wait(bar_do_empty + st, ph ^ 1);
-        mbar_arrive_expect_tx(bar_do_full + st, kTile + kT * 4);
-        for (int h = 0; h < 2; ++h) tma_load_3d(sdO + st * kTile + h * kHalf, &tmap_do, bar_do_full + st, h * 64, head, q0);
-        bulk_load_1d(sDelta + st * kT, p.delta + static_cast<int64_t>(head) * p.n_pad + q0, kT * 4, bar_do_full + st);
-        // warm L2 for the tiles two steps ahead: with only two shared-memory stages the next load cannot be
-        // issued before this step's dK retires, so its latency must be an L2 hit, not a DRAM round trip
-        if ((p.debug_flags & 16) && it + 2 < n_iter) {
-          const int head2 = kvh * p.group + (it + 2) / n_qt;
-          const int q2 = (jt + (it + 2) % n_qt) * kT;
+        bulk_load_1d(sAugQ + st * kAug, p.aug_lse + aug_off, kAug, bar_q_full + st);
+        mbar_wait(bar_do_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_do_full, kTile + kAug);
+        for (int h = 0; h < 2; ++h) tma_load_3d(sdO + h * kHalf, &tmap_do, bar_do_full, h * 64, head, q0);
+        bulk_load_1d(sAugDO, p.aug_delta + aug_off, kAug, bar_do_full);
+        // warm L2 for the tiles `l2_ahead` steps ahead: the ring cannot request them before a stage retires, so
+        // what the eventual load costs must be an L2 hit (~1.0-1.4k cycles), not a DRAM round trip (~1.9-2.6k
+        // with every SM streaming: tools/tma_bench.cu)
+        if (p.l2_ahead > 0 && it + p.l2_ahead < n_iter) {
+          const int it2 = it + p.l2_ahead;
+          const int head2 = kvh * p.group + it2 / n_qt;
+          const int q2 = (jt + it2 % n_qt) * kT;
           for (int h = 0; h < 2; ++h) {
             tma_prefetch_l2_3d(&tmap_q, h * 64, head2, q2);
             tma_prefetch_l2_3d(&tmap_do, h * 64, head2, q2);
@@ -211,6 +242,12 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint32_t nK = sdesc_lo_mnmajor(smem_u32(sK), kHalf), nQ = sdesc_lo_mnmajor(smem_u32(sQ), kHalf);
       const uint32_t nDO = sdesc_lo_mnmajor(smem_u32(sdO), kHalf), nDS = sdesc_lo_mnmajor(smem_u32(sdS), kHalf);
       constexpr uint32_t kStage = kTile >> 4;                       // next Q / dO stage
+      // broadcast k-step: un-swizzled K-major, SBO = 128 (8-row groups), LBO = distance to the shared zero chunk
+      constexpr uint32_t kAugHi = (128u >> 4) | (1u << 14);
+      const uint32_t zero_addr = smem_u32(sAugZero);
+      auto aug_lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (((zero_addr - addr) >> 4) << 16); };
+      const uint32_t aOne = aug_lo(smem_u32(sAugOne)), aDO = aug_lo(smem_u32(sAugDO)), aQ0 = aug_lo(smem_u32(sAugQ));
+      constexpr uint32_t kAugStage = (kAug >> 4) - ((kAug >> 4) << 16);   // next chunk: address up, LBO down
 #define DTA_KOFF(kk) ((((kk) >> 2) * (kHalf >> 4)) + (((kk) & 3) * 2))   /* K-major: 16 elements along the row */
 #define DTA_NOFF(kk) ((kk) * (2048 >> 4))                                /* MN-major: 16 rows of the tile     */
 
@@ -219,15 +256,17 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           const uint32_t b = kQ + st * kStage;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) umma_ss_lo(R0, kK + DTA_KOFF(kk), b + DTA_KOFF(kk), idesc_kk, kk > 0);
+          umma_ss_lohi(R0, aOne, aQ0 + st * kAugStage, kAugHi, idesc_kk, 1u);   // S^T += 1 (x) lse'
           umma_commit(bar_st_full);
         }
         __syncwarp();
       };
-      auto issue_dp = [&](uint32_t st) {       // dP^T = V dO^T
+      auto issue_dp = [&]() {                  // dP^T = V dO^T
         if (elect_one()) {
-          const uint32_t b = kDO + st * kStage;
+          const uint32_t b = kDO;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) umma_ss_lo(R1, kV + DTA_KOFF(kk), b + DTA_KOFF(kk), idesc_kk, kk > 0);
+          umma_ss_lohi(R1, aOne, aDO, kAugHi, idesc_kk, 1u);                                   // dP^T -= 1 (x) delta
           umma_commit(bar_dp_full);
         }
         __syncwarp();
@@ -237,30 +276,32 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_wait(bar_q_full + 0, 0);
       tc_fence_after();
       issue_st(0);
-      mbar_wait(bar_do_full + 0, 0);
+      mbar_wait(bar_do_full, 0);
       tc_fence_after();
-      issue_dp(0);
+      issue_dp();
 
+      uint32_t st = 0, stph = 0;               // Q stage of step it and its phase parity (it % 3, (it / 3) & 1)
       for (int it = 0; it < n_iter; ++it) {
-        const uint32_t st = it & 1;
         const bool has_next = it + 1 < n_iter;
-        const uint32_t nst = (it + 1) & 1;
-        const uint32_t nph = ((it + 1) >> 1) & 1;
+        const uint32_t nst = st + 1 == kQStages ? 0u : st + 1;
+        const uint32_t nph = st + 1 == kQStages ? stph ^ 1u : stph;
         const uint32_t not_first = it > 0 ? 1u : 0u;
         // dV += P^T dO
         mbar_wait(bar_p_full, it & 1);
         if (lane == 0) DTA_TRACE(0);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t b = nDO + st * kStage;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_ts_lo(RdV, R0 + (kk >> 2) * 64 + (kk & 3) * 8, b + DTA_NOFF(kk), idesc_kn, (kk > 0) ? 1u : not_first);
+            umma_ts_lo(RdV, R0 + (kk >> 2) * 64 + (kk & 3) * 8, nDO + DTA_NOFF(kk), idesc_kn, (kk > 0) ? 1u : not_first);
+          umma_commit(bar_do_empty);             // dO(it) has no reader left: reload it for step it+1 right away
         }
         __syncwarp();
+        if (lane == 0) DTA_TRACE(13);
         // S^T of the next step reuses R0 right behind dV (tensor pipe executes in issue order)
         if (has_next) {
           mbar_wait(bar_q_full + nst, nph);
+          if (lane == 0) DTA_TRACE(14);
           tc_fence_after();
           issue_st(nst);
         }
@@ -279,19 +320,20 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             umma_ss_lo(RdK, kDS + DTA_KOFF(kk), b + DTA_NOFF(kk), idesc_kn, (kk > 0) ? 1u : not_first);
           umma_commit(bar_ds_empty);
           umma_commit(bar_q_empty + st);
-          umma_commit(bar_do_empty + st);
         }
         __syncwarp();
         if (lane == 0) DTA_TRACE(3);
         // dP^T of the next step needs R1 back from the drain warps
         if (has_next) {
-          mbar_wait(bar_do_full + nst, nph);
+          mbar_wait(bar_do_full, (it + 1) & 1);
           mbar_wait(bar_r1_free, it & 1);
           if (lane == 0) DTA_TRACE(4);
           tc_fence_after();
-          issue_dp(nst);
+          issue_dp();
           if (lane == 0) DTA_TRACE(5);
         }
+        st = nst;
+        stph = nph;
       }
       if (elect_one()) umma_commit(bar_dkv_full);
       __syncwarp();
@@ -310,15 +352,10 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     for (int it = 0; it < n_iter; ++it) {
       const int qt = jt + it % n_qt;
       const int qbase = qt * kT + ch * 64;
-      const int st = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
       const bool partial = !(qt > jt && kmin_end >= (qt + 1) * kT);
-      const float* lse = sLse + st * kT + ch * 64;
-      const float* dlt = sDelta + st * kT + ch * 64;
       const int vis_lo = k_idx - qbase, vis_hi = k_end - qbase;      // visible columns of this row: [lo, hi)
 
       // ---- P^T = exp2(S^T * scale_log2 - lse * log2e), masked -------------------------
-      mbar_wait(bar_q_full + st, ph);      // LSE tile landed
       mbar_wait(bar_st_full, it & 1);
       if (threadIdx.x == 0) DTA_TRACE(6);
       tc_fence_after();
@@ -326,34 +363,24 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tmem_ld_x32(R0 + lane_addr + ch * 64, reinterpret_cast<uint32_t*>(pr));
       tmem_ld_x32(R0 + lane_addr + ch * 64 + 32, reinterpret_cast<uint32_t*>(pr) + 32);
       tmem_ld_wait();
-      // pr = scale * P^T = 2^(s*scale_log2 + log2(scale) - lse2); the 1/scale is undone once, in the dV
-      // epilogue, so that dS^T = pr * (dP^T - delta) needs no further multiply.  Two code copies: tiles
-      // the ancestor mask leaves untouched pay nothing for it (a predicated select still costs its
-      // issue slot, and most tiles of a deep trie are mask-free).
+      // The MMA already added the per-query exponent offset (broadcast k-step), so
+      // pr = scale * P^T = 2^(S'^T * scale_log2) with no per-column operand: the 64 lse values every thread used
+      // to pull through LDS (4 wavefronts per LDS.128, broadcast or not) were ~1k of the ~5k data-pipe cycles of
+      // a step, on a pipe the UMMA operand fetch saturates by itself.  The 1/scale is undone once, in the dV
+      // epilogue, so that dS^T = pr * dP'^T needs no further multiply.  Two code copies: tiles the ancestor
+      // mask leaves untouched pay nothing for it.
       if (!partial) {
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          const float4 l4 = reinterpret_cast<const float4*>(lse)[c4];
-          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c4 * 4 + u;
-            const float x = fmaf(pr[c], p.scale_log2, lv[u]);
-            pr[c] = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
-          }
+        for (int c = 0; c < 64; ++c) {
+          const float x = pr[c] * p.scale_log2;
+          pr[c] = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
         }
       } else {
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          const float4 l4 = reinterpret_cast<const float4*>(lse)[c4];
-          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c4 * 4 + u;
-            const float x = fmaf(pr[c], p.scale_log2, lv[u]);
-            const float v = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
-            pr[c] = (c >= vis_lo && c < vis_hi) ? v : 0.f;
-          }
+        for (int c = 0; c < 64; ++c) {
+          const float x = pr[c] * p.scale_log2;
+          const float v = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
+          pr[c] = (c >= vis_lo && c < vis_hi) ? v : 0.f;
         }
       }
       {
@@ -368,26 +395,23 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (lane == 0) mbar_arrive(bar_p_full);          // one arrival per warp
       if (threadIdx.x == 0) DTA_TRACE(7);
 
-      // ---- dS^T = P^T o (dP^T - delta) * scale -> smem (bf16, 128B-swizzled) ----------
-      mbar_wait(bar_do_full + st, ph);     // delta tile landed
+      // ---- dS^T = (scale P^T) o dP'^T -> smem (bf16, 128B-swizzled) --------------------
       mbar_wait(bar_dp_full, it & 1);
       if (threadIdx.x == 0) DTA_TRACE(8);
       tc_fence_after();
       uint32_t dsp[32];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {        // two 32-column halves: delta loads overlap the TMEM load
-        float dp[32];
-        tmem_ld_x32(R1 + lane_addr + ch * 64 + hf * 32, reinterpret_cast<uint32_t*>(dp));
-        float4 d4[8];
+      {                                       // dP'^T = dP^T - delta already (broadcast k-step); two 32-column halves
+        float dp0[32], dp1[32];
+        tmem_ld_x32(R1 + lane_addr + ch * 64, reinterpret_cast<uint32_t*>(dp0));
+        tmem_ld_wait();
+        tmem_ld_x32(R1 + lane_addr + ch * 64 + 32, reinterpret_cast<uint32_t*>(dp1));   // in flight under the math below
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d4[i] = reinterpret_cast<const float4*>(dlt)[hf * 8 + i];
+        for (int i = 0; i < 16; ++i) dsp[i] = pack_bf16x2(pr[2 * i] * dp0[2 * i], pr[2 * i + 1] * dp0[2 * i + 1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = hf * 32 + i * 4;
-          dsp[hf * 16 + i * 2] = pack_bf16x2(pr[c] * (dp[i * 4] - d4[i].x), pr[c + 1] * (dp[i * 4 + 1] - d4[i].y));
-          dsp[hf * 16 + i * 2 + 1] = pack_bf16x2(pr[c + 2] * (dp[i * 4 + 2] - d4[i].z), pr[c + 3] * (dp[i * 4 + 3] - d4[i].w));
-        }
+        for (int i = 0; i < 16; ++i)
+          dsp[16 + i] = pack_bf16x2(pr[32 + 2 * i] * dp1[2 * i], pr[32 + 2 * i + 1] * dp1[2 * i + 1]);
       }
       tc_fence_before();                   // our R1 reads are done before the arrive below
       if (it > 0) mbar_wait(bar_ds_empty, (it - 1) & 1);
@@ -462,8 +486,46 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // is the proper fix but needs 16-64 KB of staging this kernel does not have.
       float* dst = p.dq_accum + (static_cast<int64_t>(q0) * p.n_q_heads + head) * kT + d;
       const int64_t row = static_cast<int64_t>(p.n_q_heads) * kT;
-      const int n_valid = (p.debug_flags & 1) ? 0 : min(kT, p.n_nodes - q0);
-      if (n_valid == kT) {
+      const int n_valid = min(kT, p.n_nodes - q0);
+      if (kDqTma) {
+        // Each drain warp owns 32 head-dim lanes = one 128-byte column block of the dq rows.  It stages kDqRows
+        // query rows at a time ([rows][32 floats], conflict-free STS.32) in one of its two private buffers and
+        // hands them to the TMA unit as ONE tensor reduce-add; no other warp is involved, so the only
+        // synchronisation is __syncwarp + the bulk-group read fence of the issuing lane.  512 reds per step and
+        // SM (one 128-byte red per ~5 LSU cycles, all step long) become 512 single-wavefront stores + 32 TMA ops.
+        float* stage = reinterpret_cast<float*>(smem + BwdSmem::dq_stage) + (warp & 3) * (2 * kDqRows * 32);
+        const int c0 = head * kT + ((warp & 3) << 5);
+#pragma unroll
+        for (int ck = 0; ck < kT / kDqRows; ++ck) {
+          float* buf = stage + (ck & 1) * (kDqRows * 32);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer of chunk ck-2 is free
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < kDqRows; ++r) buf[r * 32 + lane] = acc[ck * kDqRows + r];
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile(
+                "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                    reinterpret_cast<uint64_t>(&tmap_dq)),
+                "r"(c0), "r"(q0 + ck * kDqRows), "r"(smem_u32(buf))
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else if (p.debug_flags & 1) {
+        // ablation: no reds
+      } else if (n_valid == kT && p.red_gap > 0) {
+        // rate-matched issue: the SM retires one 128-byte red per ~5 cycles (measured, tools/red_bench.cu), i.e.
+        // one per ~20 cycles per drain warp.  Issuing faster only fills the per-scheduler MIO queue, and every
+        // LDS / STS / MUFU of the compute warps on that scheduler then waits behind the queued reds.
+        uint32_t pace = lane;
+#pragma unroll
+        for (int c = 0; c < kT; ++c) {
+          red_add_f32(dst + c * row, acc[c]);
+          for (int g = 0; g < p.red_gap; ++g) asm volatile("mad.lo.u32 %0, %0, %0, %0;" : "+r"(pace));
+        }
+      } else if (n_valid == kT) {
 #pragma unroll
         for (int c = 0; c < kT; ++c) red_add_f32(dst + c * row, acc[c]);
       } else {
@@ -473,6 +535,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       if (threadIdx.x == 256) DTA_TRACE(12);
     }
+    if (kDqTma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -484,14 +547,28 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------
-// delta[h, q] = sum_d dO[q,h,d] * O[q,h,d]      (one warp per (q, h) row; HBM-bound)
+// Pre-pass (one warp per (q, h) row; HBM-bound): delta[h, q] = sum_d dO[q,h,d] * O[q,h,d] and the exponent
+// offset L = (log2(scale) - lse2[h, q]) / scale_log2, each written as a 3-term bf16 split into a 16-byte
+// row {hi, mid, lo, 0, 0, 0, 0, 0} -- the B operand rows of the main kernel's broadcast k-step, which
+// computes S'^T = S^T + L and dP'^T = dP^T - delta on the tensor core (products with 1.0 are exact and
+// the fp32 accumulator keeps all 24 bits of the three terms).
 // ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 split3_bf16(float x) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h);
+  const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(m);
+  const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+  const uint32_t w0 = static_cast<uint32_t>(__bfloat16_as_ushort(h)) | (static_cast<uint32_t>(__bfloat16_as_ushort(m)) << 16);
+  return make_uint4(w0, static_cast<uint32_t>(__bfloat16_as_ushort(l)), 0u, 0u);
+}
+
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ out,
                                                          const __nv_bfloat16* __restrict__ dout, int n_nodes,
                                                          int n_pad, int n_heads, int64_t row_stride,
-                                                         int64_t head_stride, float* __restrict__ delta,
-                                                         const float* __restrict__ lse2, float lshift,
-                                                         float* __restrict__ lse_shift) {
+                                                         int64_t head_stride, const float* __restrict__ lse2,
+                                                         float lshift, float inv_scale_log2,
+                                                         uint4* __restrict__ aug_lse, uint4* __restrict__ aug_delta) {
   const int lane = threadIdx.x & 31;
   const int64_t n_rows = static_cast<int64_t>(n_pad) * n_heads;
   for (int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; w < n_rows;
@@ -514,8 +591,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
       const int64_t o = static_cast<int64_t>(h) * n_pad + q;
-      delta[o] = acc;
-      lse_shift[o] = q < n_nodes ? lshift - lse2[o] : 0.f;      // exponent offset used by the main kernel
+      aug_delta[o] = split3_bf16(-acc);
+      aug_lse[o] = split3_bf16(q < n_nodes ? (lshift - lse2[o]) * inv_scale_log2 : 0.f);
     }
   }
 }
@@ -556,8 +633,8 @@ int dta_debug_set_bwd_trace(long long* buf) { g_bwd_trace = buf; return 0; }
 size_t dta_tree_attn_bwd_workspace_bytes(const dta_attn_shape_t* sh) {
   if (!sh) return 0;
   const size_t dq = static_cast<size_t>(sh->n_pad) * sh->n_q_heads * kT * sizeof(float);
-  const size_t delta = static_cast<size_t>(sh->n_pad) * sh->n_q_heads * sizeof(float);
-  return dq + 2 * delta + 256;
+  const size_t aug = static_cast<size_t>(sh->n_pad) * sh->n_q_heads * 16;     // one 16-byte operand row per (head, query)
+  return dq + 2 * aug + 256;
 }
 
 int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
@@ -583,8 +660,8 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
 
   float* dq_accum = static_cast<float*>(workspace);
   const size_t dq_bytes = static_cast<size_t>(sh->n_pad) * sh->n_q_heads * kT * sizeof(float);
-  float* delta = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + dq_bytes);
-  float* lse_shift = delta + static_cast<size_t>(sh->n_pad) * sh->n_q_heads;
+  uint4* aug_lse = reinterpret_cast<uint4*>(static_cast<uint8_t*>(workspace) + dq_bytes);
+  uint4* aug_delta = aug_lse + static_cast<size_t>(sh->n_pad) * sh->n_q_heads;
   DTA_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, dq_bytes, stream));
 
   const int64_t n_rows = static_cast<int64_t>(sh->n_pad) * sh->n_q_heads;
@@ -594,7 +671,8 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
     if (grid > cap) grid = cap;
     attn_delta_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), sh->n_nodes, sh->n_pad,
-        sh->n_q_heads, sh->o_row_stride, sh->o_head_stride, delta, lse, log2f(sh->scale), lse_shift);
+        sh->n_q_heads, sh->o_row_stride, sh->o_head_stride, lse, log2f(sh->scale), 1.0f / (sh->scale * kLog2e),
+        aug_lse, aug_delta);
     DTA_CHECK_CUDA(cudaGetLastError());
   }
 
@@ -604,10 +682,12 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   if ((rc = make_tmap_bf16_rows(&tk, k, sh->n_nodes, sh->n_kv_heads, kT, sh->k_row_stride, sh->k_head_stride, kT))) return rc;
   if ((rc = make_tmap_bf16_rows(&tv, v, sh->n_nodes, sh->n_kv_heads, kT, sh->v_row_stride, sh->v_head_stride, kT))) return rc;
   if ((rc = make_tmap_bf16_rows(&tdo, dout, sh->n_nodes, sh->n_q_heads, kT, sh->o_row_stride, sh->o_head_stride, kT))) return rc;
+  CUtensorMap tdq;
+  if ((rc = make_tmap_f32_2d(&tdq, dq_accum, static_cast<int64_t>(sh->n_q_heads) * kT, sh->n_pad, 32, kDqRows))) return rc;
 
   BwdParams p;
-  p.lse = lse_shift;
-  p.delta = delta;
+  p.aug_lse = reinterpret_cast<const __nv_bfloat16*>(aug_lse);
+  p.aug_delta = reinterpret_cast<const __nv_bfloat16*>(aug_delta);
   p.dq_accum = dq_accum;
   p.dk = static_cast<__nv_bfloat16*>(dk);
   p.dv = static_cast<__nv_bfloat16*>(dv);
@@ -627,23 +707,29 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   p.scale = sh->scale;
   p.scale_log2 = sh->scale * kLog2e;
   p.inv_scale = 1.0f / sh->scale;
+  p.l2_ahead = getenv("DTA_BWD_L2PF") ? atoi(getenv("DTA_BWD_L2PF")) : kDefaultL2Ahead;
+  p.red_gap = getenv("DTA_BWD_REDGAP") ? atoi(getenv("DTA_BWD_REDGAP")) : kDefaultRedGap;
   p.debug_flags = getenv("DTA_DEBUG_FLAGS") ? atoi(getenv("DTA_DEBUG_FLAGS")) : 0;
   p.trace = g_bwd_trace;
 
-  using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const BwdParams);
+  using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                          const BwdParams);
   static Kernel kernel = nullptr;
   if (!kernel) {
-    // share of the exponentials computed on the FMA pipes; DTA_BWD_POLY (0..4 of every 8) is a tuning knob
+    // tuning knobs: DTA_BWD_POLY = share (of 8) of the exponentials computed on the FMA pipes; DTA_BWD_DQ_TMA = 0
+    // selects the per-lane red path for dQ instead of the TMA tensor reduce
     const char* e = getenv("DTA_BWD_POLY");
     const int poly = e ? atoi(e) : kDefaultBwdPoly;
-    kernel = poly <= 0 ? tree_attn_bwd_kernel<0> : poly == 1 ? tree_attn_bwd_kernel<1>
-           : poly == 2 ? tree_attn_bwd_kernel<2> : poly == 3 ? tree_attn_bwd_kernel<3> : tree_attn_bwd_kernel<4>;
+    const char* t = getenv("DTA_BWD_DQ_TMA");
+    const bool dq_tma = t ? atoi(t) != 0 : kDefaultDqTma;
+    kernel = dq_tma ? (poly <= 0 ? tree_attn_bwd_kernel<0, true> : poly <= 2 ? tree_attn_bwd_kernel<2, true> : tree_attn_bwd_kernel<4, true>)
+                    : (poly <= 0 ? tree_attn_bwd_kernel<0, false> : poly <= 2 ? tree_attn_bwd_kernel<2, false> : tree_attn_bwd_kernel<4, false>);
     DTA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::total));
   }
   const int n_tiles = sh->n_pad / DTA_TILE;
   const ProfileHook hook = take_profile_hook();
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
-  kernel<<<n_tiles * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, p);
+  kernel<<<n_tiles * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, tdq, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
 

@@ -53,6 +53,22 @@ int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int he
   return DTA_OK;
 }
 
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int box_cols, int box_rows) {
+  auto enc = encode_fn();
+  if (!enc) return set_error(DTA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (cols * 4) % 16 != 0)
+    return set_error(DTA_ERR_INVALID, "fp32 tensor base / row pitch must be 16-byte aligned");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DTA_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 2-D) failed with CUresult %d", (int)r);
+  return DTA_OK;
+}
+
 static thread_local ProfileHook g_hook;
 ProfileHook take_profile_hook() {
   ProfileHook h = g_hook;

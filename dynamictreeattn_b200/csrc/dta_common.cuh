@@ -36,6 +36,9 @@ int set_error(int code, const char* fmt, ...);
 int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int heads, int head_dim,
                         int64_t row_stride, int64_t head_stride, int box_rows);
 
+// fp32 row-major [rows][cols] tensor, box = (box_cols, box_rows), no swizzle (target of the dQ tensor reduce)
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int box_cols, int box_rows);
+
 int sm_count();
 
 // one-shot profiling events armed by dta_profile_next_attn (thread-local)

@@ -141,6 +141,17 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t saddr, uint32_t lb
   return d;
 }
 
+// Un-swizzled K-major operand: 8-row x 16-byte core matrices, each 128 contiguous bytes.
+//   LBO = byte distance between core matrices adjacent along K, SBO = between 8-row groups along M/N.
+__device__ __forceinline__ uint64_t make_sdesc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   [4,6) c_format=1 (f32)  [7,10) a_format=1 (bf16)  [10,13) b_format=1 (bf16)
 //   [15] a_major (0=K,1=MN) [16] b_major  [17,23) N>>3  [24,29) M>>4
@@ -187,6 +198,18 @@ __device__ __forceinline__ void umma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint3
       "mov.b64 db, {%2, %5};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kSdescHi)
+      : "memory");
+}
+// Same with an explicit descriptor `hi` word (operands that are not 128B-swizzled tiles)
+__device__ __forceinline__ void umma_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
       : "memory");
 }
 __device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc,

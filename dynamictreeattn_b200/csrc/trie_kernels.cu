@@ -352,8 +352,8 @@ int dta_tile_meta(const int32_t* subtree_end, const int32_t* depth, int n_nodes,
   tile_minmax_kernel<<<(n_tiles * 32 + 255) / 256, 256, 0, stream>>>(
       subtree_end, depth, n_nodes, n_tiles, kmax_end, kmin_end, reinterpret_cast<unsigned long long*>(pair_count));
   DTA_CHECK_CUDA(cudaGetLastError());
-  const char* kb = getenv("DTA_K_ORDER_BUCKET");      // experiment: coarser weight classes keep DFS neighbours together
-  const int k_bucket = kb && atoi(kb) > 0 ? atoi(kb) : 1;
+  const char* kb = getenv("DTA_K_ORDER_BUCKET");      // tuning override of the weight-class width (tests use the default)
+  const int k_bucket = kb && atoi(kb) > 0 ? atoi(kb) : DTA_K_ORDER_BUCKET;
   tile_order_kernel<<<1, 1024, 0, stream>>>(kmax_end, n_tiles, q_order, q_nlive, k_order, k_qlast, k_bucket);
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;

@@ -218,7 +218,7 @@ class TreeTrainingEngine:
 
     def _can_keep_logits(self, n_rows: int, vocab: int, elem: int, dev) -> bool:
         """True when all logits chunks of one step fit in free HBM with a 24 GB margin."""
-        if not self.keep_head_logits:
+        if not self.keep_head_logits or torch.device(dev).type != "cuda":
             return False
         free, _ = torch.cuda.mem_get_info(dev)
         free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)

@@ -70,9 +70,13 @@ int dta_trie_paths(const int32_t* lens, const int32_t* lcp, const int32_t* leaf_
  *   kmax_end[t], kmin_end[t] : max / min of subtree_end over the VALID keys of tile t
  *   q_order[n_tiles]         : query tiles sorted by number of live key tiles, descending
  *   q_nlive[n_tiles]         : that number, indexed by tile
- *   k_order[n_tiles]         : key tiles sorted by number of live query tiles, descending
+ *   k_order[n_tiles]         : key tiles sorted by weight CLASS = (live query tiles - 1) / DTA_K_ORDER_BUCKET,
+ *                              descending, ties in tile (= DFS) order: heavy tiles first for load balance, but
+ *                              neighbours of one subtree stay adjacent, so the CTAs resident at the same time
+ *                              walk the same query tiles and their Q / dO loads and dQ reductions meet in L2
  *   k_qlast[n_tiles]         : last live query tile of key tile t (live range is [t, k_qlast[t]])
  *   pair_count[1] (int64)    : number of visible (q,k) pairs = sum(depth)+N */
+#define DTA_K_ORDER_BUCKET 64
 int dta_tile_meta(const int32_t* subtree_end, const int32_t* depth, int n_nodes, int n_pad,
                   int32_t* kmax_end, int32_t* kmin_end, int32_t* q_order, int32_t* q_nlive, int32_t* k_order,
                   int32_t* k_qlast, int64_t* pair_count, dta_stream_t stream);

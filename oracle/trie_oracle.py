@@ -238,6 +238,9 @@ def interval_mask(subtree_end: np.ndarray) -> np.ndarray:
     return (k <= q) & (q < subtree_end[None, :])
 
 
+K_ORDER_BUCKET = 64     # include/dta_b200.h DTA_K_ORDER_BUCKET
+
+
 def tile_meta(subtree_end: np.ndarray, tile: int = 128):
     """Per-tile summaries the kernels consume (see include/dta_b200.h dta_tile_meta)."""
     N = len(subtree_end)
@@ -251,6 +254,6 @@ def tile_meta(subtree_end: np.ndarray, tile: int = 128):
     k_qlast = (kmax - 1) // tile
     k_work = k_qlast - np.arange(n_tiles)
     q_order = np.array(sorted(range(n_tiles), key=lambda i: (-q_nlive[i], i)), dtype=np.int64)
-    k_order = np.array(sorted(range(n_tiles), key=lambda i: (-k_work[i], i)), dtype=np.int64)
+    k_order = np.array(sorted(range(n_tiles), key=lambda i: (-(k_work[i] // K_ORDER_BUCKET), i)), dtype=np.int64)
     return {"kmax_end": kmax, "kmin_end": kmin, "q_nlive": q_nlive, "k_qlast": k_qlast,
             "q_order": q_order, "k_order": k_order}

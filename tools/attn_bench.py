@@ -73,6 +73,7 @@ def run_case(name, seqs, iters, Hq=16, Hkv=8, permute="backward"):
     attention.PROFILE = None
     f, b = statistics.median(fwd), statistics.median(bwd)
     res = {"case": name, "N": N, "leaves": lay.n_leaf, "pairs": P, "fwd_ms": round(f, 3), "bwd_ms": round(b, 3),
+           "fwd_min_ms": round(min(fwd), 3), "bwd_min_ms": round(min(bwd), 3),
            "fwd_tflops": round(4 * P * Hq * 128 / f / 1e9, 1), "bwd_tflops": round(10 * P * Hq * 128 / b / 1e9, 1),
            "fwd_bwd_tflops": round(14 * P * Hq * 128 / (f + b) / 1e9, 1)}
     print(json.dumps(res), flush=True)

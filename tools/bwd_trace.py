@@ -24,9 +24,9 @@ tree_attention(q, k, v, lay).backward(do)
 torch.cuda.synchronize()
 raw.dta_debug_set_bwd_trace(None)
 t = buf.cpu().view(48, 16)
-names = ["p_full", "dV+St issued", "ds_full", "dQ+dK issued", "r1_free", "dP issued", "C:st_full", "C:P done", "C:dp_full", "C:dS done", "D:dq_full", "D:ld done", "D:red issued"]
+names = ["p_full", "dV+St issued", "ds_full", "dQ+dK issued", "r1_free", "dP issued", "C:st_full", "C:P done", "C:dp_full", "C:dS done", "D:dq_full", "D:ld done", "D:red issued", "dV issued", "q_full seen"]
 t0 = int(t[2, 0])
 for it in range(2, 12):
-    print(f"step {it}: " + "  ".join(f"{names[e]}={int(t[it, e]) - t0}" for e in range(13)))
+    print(f"step {it}: " + "  ".join(f"{names[e]}={int(t[it, e]) - t0}" for e in range(15)))
     t0 = int(t[it, 0])
 print("period (p_full to p_full):", [int(t[i + 1, 0] - t[i, 0]) for i in range(2, 20)])
