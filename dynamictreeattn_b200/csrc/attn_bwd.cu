@@ -20,7 +20,7 @@
 //                computed transposed so that TMEM lanes = key rows: the ancestor mask is
 //                then a per-thread column RANGE test [k, subtree_end[k]).
 //   warp roles = warps 0-7 compute (lane = key row, two column halves) | warps 8-11 dQ drain
-//                (lane = head-dim index) | warp 14 TMA producer | warp 15 MMA issuer + TMEM owner.
+//                (lane = head-dim index) | warp 14 TMA producer | warps 15 and 13 MMA issuers (15 owns TMEM).
 //                The issuer sits in the highest warp slot: the SM arbiter favours high warp ids
 //                and the issuer is the one warp whose latency is on every critical path.
 //   TMEM       = R0 S^T/P^T [0,128) (P^T bf16: queries 0-63 in cols [0,32), 64-127 in cols [64,96))
@@ -37,8 +37,9 @@ static constexpr int kT = 128;                       // tile edge (queries, keys
 static constexpr int kHalf = kT * 128;               // [128 rows][64 bf16] swizzled half tile, bytes
 static constexpr int kTile = 2 * kHalf;              // 32 KB
 static constexpr int kBwdThreads = 512;
-static constexpr int kProducerWarp = 14, kMmaWarp = 15;
+static constexpr int kProducerWarp = 14, kMmaWarp = 15, kMmaWarpB = 13;
 static constexpr int kQStages = 2;                   // Q ring depth
+static constexpr int kDqBufs = 3;                    // staging buffers per drain warp (reduces in flight)
 static constexpr int kDqRows = 16;                   // query rows per dQ reduce box (2 KB per warp and buffer)
 static constexpr int kAug = kT * 16;                 // one un-swizzled [128][8 bf16] K-chunk, bytes
 static constexpr float kLog2e = 1.4426950408889634f;
@@ -58,9 +59,9 @@ struct BwdSmem {
   static constexpr int aug_do = aug_q + kQStages * kAug;   // 1 chunk: per-query -(delta hi, mid, lo, 0...)
   static constexpr int aug_one = aug_do + kAug;       // 1 chunk: (1, 1, 1, 0...) in every row
   static constexpr int aug_zero = aug_one + kAug;     // 1 chunk of zeros = k columns 8..15 of all of the above
-  // dQ staging for the bulk tensor reduce: per drain warp two [kDqRows queries][32 floats] buffers
+  // dQ staging for the bulk tensor reduce: per drain warp kDqBufs [kDqRows queries][32 floats] buffers
   static constexpr int dq_stage = aug_zero + kAug;
-  static constexpr int bars = dq_stage + 4 * 2 * kDqRows * 128;
+  static constexpr int bars = dq_stage + 4 * kDqBufs * kDqRows * 128;
   static constexpr int n_bars = 1 + 2 * kQStages + 2 + 8;
   static constexpr int misc = bars + n_bars * 8;
   static constexpr int total = misc + 16;
@@ -123,7 +124,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* bar_p_full = bar_st_full + 1;             // P^T written (8 warp arrivals)
   uint64_t* bar_dp_full = bar_p_full + 1;             // dP^T ready
   uint64_t* bar_ds_full = bar_dp_full + 1;            // dS^T in smem (8 warp arrivals)
-  uint64_t* bar_ds_empty = bar_ds_full + 1;           // dK/dQ MMAs of the step done -> sdS reusable
+  uint64_t* bar_ds_empty = bar_ds_full + 1;           // (unused: implied by dp_full, see the dS^T pass)
   uint64_t* bar_dq_full = bar_ds_empty + 1;           // dQ tile ready in R1
   uint64_t* bar_r1_free = bar_dq_full + 1;            // dQ tile copied out of R1 (4 warp arrivals)
   uint64_t* bar_dkv_full = bar_r1_free + 1;           // everything done
@@ -164,7 +165,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_init(bar_q_empty + s, 1);
       }
       mbar_init(bar_do_full, 1);
-      mbar_init(bar_do_empty, 1);
+      mbar_init(bar_do_empty, 2);          // dP^T (issuer B) and dV (issuer A) both retired
       mbar_init(bar_st_full, 1);
       mbar_init(bar_p_full, 8);
       mbar_init(bar_dp_full, 1);
@@ -172,7 +173,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_init(bar_ds_empty, 1);
       mbar_init(bar_dq_full, 1);
       mbar_init(bar_r1_free, 4);
-      mbar_init(bar_dkv_full, 1);
+      mbar_init(bar_dkv_full, 2);          // both issuing warps
       fence_mbar_init();
     }
     __syncwarp();
@@ -224,13 +225,19 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ================================ MMA issuer =========================================
+  } else if (warp == kMmaWarp || warp == kMmaWarpB) {
+    // ================================ MMA issuers ========================================
+    // TWO issuing warps, one per dependency loop of a step, so that a wait in one loop never holds back the
+    // MMAs of the other (one in-order issuer spent ~1.3k of ~4.4k cycles per step blocked on the wrong loop's
+    // barrier while the tensor pipe idled):
+    //   warp A (kMmaWarp) : wait P^T(it)  -> dV(it)  -> wait Q(it+1) -> S^T(it+1)                  [TMEM R0 loop]
+    //   warp B (kMmaWarpB): wait dS^T(it) -> dQ^T(it), dK(it) -> wait dO(it+1), R1 drained -> dP^T(it+1)  [R1 loop]
+    // The tensor pipe executes tcgen05.mma in arrival order whichever warp sent them; the two streams touch
+    // disjoint accumulators (A: R0, dV; B: R1, dK), and every hazard between them goes through a compute-warp
+    // barrier (S^T -> P^T -> dS^T).  dO(it) is read by dP^T(it) (B) and dV(it) (A): bar_do_empty counts both.
+    // In each warp the WHOLE warp runs the loop (waits are warp-uniform) and only the tcgen05 instructions are
+    // predicated on one elected lane, so descriptor arithmetic stays on the uniform datapath.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    // The WHOLE warp runs this loop (waits are warp-uniform) and only the tcgen05 instructions are
-    // predicated on one elected lane: descriptor arithmetic then stays on the uniform datapath instead
-    // of costing a vector->uniform register move per operand, which made issue (not the tensor pipe)
-    // the limiter when a single divergent thread ran the loop.
     {
       constexpr uint32_t idesc_kk = make_idesc_bf16(kT, kT, false, false);   // S^T, dP^T
       constexpr uint32_t idesc_kn = make_idesc_bf16(kT, kT, false, true);    // dV, dK (B MN-major)
@@ -241,7 +248,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint32_t kDS = sdesc_lo_kmajor(smem_u32(sdS));
       const uint32_t nK = sdesc_lo_mnmajor(smem_u32(sK), kHalf), nQ = sdesc_lo_mnmajor(smem_u32(sQ), kHalf);
       const uint32_t nDO = sdesc_lo_mnmajor(smem_u32(sdO), kHalf), nDS = sdesc_lo_mnmajor(smem_u32(sdS), kHalf);
-      constexpr uint32_t kStage = kTile >> 4;                       // next Q / dO stage
+      constexpr uint32_t kStage = kTile >> 4;                       // next Q stage
       // broadcast k-step: un-swizzled K-major, SBO = 128 (8-row groups), LBO = distance to the shared zero chunk
       constexpr uint32_t kAugHi = (128u >> 4) | (1u << 14);
       const uint32_t zero_addr = smem_u32(sAugZero);
@@ -251,91 +258,101 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #define DTA_KOFF(kk) ((((kk) >> 2) * (kHalf >> 4)) + (((kk) & 3) * 2))   /* K-major: 16 elements along the row */
 #define DTA_NOFF(kk) ((kk) * (2048 >> 4))                                /* MN-major: 16 rows of the tile     */
 
-      auto issue_st = [&](uint32_t st) {       // S^T = K Q^T
-        if (elect_one()) {
-          const uint32_t b = kQ + st * kStage;
+      if (warp == kMmaWarp) {
+        // ------------------------------ warp A: dV, S^T ------------------------------------
+        auto issue_st = [&](uint32_t st) {       // S^T = K Q^T
+          if (elect_one()) {
+            const uint32_t b = kQ + st * kStage;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) umma_ss_lo(R0, kK + DTA_KOFF(kk), b + DTA_KOFF(kk), idesc_kk, kk > 0);
-          umma_ss_lohi(R0, aOne, aQ0 + st * kAugStage, kAugHi, idesc_kk, 1u);   // S^T += 1 (x) lse'
-          umma_commit(bar_st_full);
-        }
-        __syncwarp();
-      };
-      auto issue_dp = [&]() {                  // dP^T = V dO^T
-        if (elect_one()) {
-          const uint32_t b = kDO;
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) umma_ss_lo(R1, kV + DTA_KOFF(kk), b + DTA_KOFF(kk), idesc_kk, kk > 0);
-          umma_ss_lohi(R1, aOne, aDO, kAugHi, idesc_kk, 1u);                                   // dP^T -= 1 (x) delta
-          umma_commit(bar_dp_full);
-        }
-        __syncwarp();
-      };
-
-      mbar_wait(bar_kv_full, 0);
-      mbar_wait(bar_q_full + 0, 0);
-      tc_fence_after();
-      issue_st(0);
-      mbar_wait(bar_do_full, 0);
-      tc_fence_after();
-      issue_dp();
-
-      uint32_t st = 0, stph = 0;               // Q stage of step it and its phase parity (it % 3, (it / 3) & 1)
-      for (int it = 0; it < n_iter; ++it) {
-        const bool has_next = it + 1 < n_iter;
-        const uint32_t nst = st + 1 == kQStages ? 0u : st + 1;
-        const uint32_t nph = st + 1 == kQStages ? stph ^ 1u : stph;
-        const uint32_t not_first = it > 0 ? 1u : 0u;
-        // dV += P^T dO
-        mbar_wait(bar_p_full, it & 1);
-        if (lane == 0) DTA_TRACE(0);
+            for (int kk = 0; kk < 8; ++kk) umma_ss_lo(R0, kK + DTA_KOFF(kk), b + DTA_KOFF(kk), idesc_kk, kk > 0);
+            umma_ss_lohi(R0, aOne, aQ0 + st * kAugStage, kAugHi, idesc_kk, 1u);   // S^T += 1 (x) lse'
+            umma_commit(bar_st_full);
+          }
+          __syncwarp();
+        };
+        mbar_wait(bar_kv_full, 0);
+        mbar_wait(bar_q_full + 0, 0);
         tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ts_lo(RdV, R0 + (kk >> 2) * 64 + (kk & 3) * 8, nDO + DTA_NOFF(kk), idesc_kn, (kk > 0) ? 1u : not_first);
-          umma_commit(bar_do_empty);             // dO(it) has no reader left: reload it for step it+1 right away
-        }
-        __syncwarp();
-        if (lane == 0) DTA_TRACE(13);
-        // S^T of the next step reuses R0 right behind dV (tensor pipe executes in issue order)
-        if (has_next) {
-          mbar_wait(bar_q_full + nst, nph);
-          if (lane == 0) DTA_TRACE(14);
+        issue_st(0);
+        uint32_t st = 0, stph = 0;               // Q stage of step it and its phase parity
+        for (int it = 0; it < n_iter; ++it) {
+          const bool has_next = it + 1 < n_iter;
+          const uint32_t nst = st + 1 == kQStages ? 0u : st + 1;
+          const uint32_t nph = st + 1 == kQStages ? stph ^ 1u : stph;
+          const uint32_t not_first = it > 0 ? 1u : 0u;
+          // dV += P^T dO
+          mbar_wait(bar_p_full, it & 1);
+          if (lane == 0) DTA_TRACE(0);
+          mbar_wait(bar_do_full, it & 1);          // dO(it) landed (warp B checked it for dP^T(it); this warp has not)
           tc_fence_after();
-          issue_st(nst);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ts_lo(RdV, R0 + (kk >> 2) * 64 + (kk & 3) * 8, nDO + DTA_NOFF(kk), idesc_kn, (kk > 0) ? 1u : not_first);
+            umma_commit(bar_do_empty);             // this warp's half of "dO(it) has no reader left"
+          }
+          __syncwarp();
+          if (lane == 0) DTA_TRACE(13);
+          // S^T of the next step reuses R0 right behind dV (tensor pipe executes one warp's MMAs in issue order)
+          if (has_next) {
+            mbar_wait(bar_q_full + nst, nph);
+            if (lane == 0) DTA_TRACE(14);
+            tc_fence_after();
+            issue_st(nst);
+          }
+          if (lane == 0) DTA_TRACE(1);
+          st = nst;
+          stph = nph;
         }
-        // dQ^T = K^T dS^T (first, so the drain overlaps dK), dK += dS^T Q
-        if (lane == 0) DTA_TRACE(1);
-        mbar_wait(bar_ds_full, it & 1);
-        if (lane == 0) DTA_TRACE(2);
+      } else {
+        // ------------------------------ warp B: dP^T, dQ^T, dK -------------------------------
+        auto issue_dp = [&]() {                  // dP^T = V dO^T
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) umma_ss_lo(R1, kV + DTA_KOFF(kk), kDO + DTA_KOFF(kk), idesc_kk, kk > 0);
+            umma_ss_lohi(R1, aOne, aDO, kAugHi, idesc_kk, 1u);                                   // dP^T -= 1 (x) delta
+            umma_commit(bar_dp_full);
+            umma_commit(bar_do_empty);           // this warp's half of "dO(it) has no reader left"
+          }
+          __syncwarp();
+        };
+        mbar_wait(bar_kv_full, 0);
+        mbar_wait(bar_do_full, 0);
         tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) umma_ss_lo(R1, nK + DTA_NOFF(kk), nDS + DTA_NOFF(kk), idesc_nn, kk > 0);
-          umma_commit(bar_dq_full);
-          const uint32_t b = nQ + st * kStage;
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ss_lo(RdK, kDS + DTA_KOFF(kk), b + DTA_NOFF(kk), idesc_kn, (kk > 0) ? 1u : not_first);
-          umma_commit(bar_ds_empty);
-          umma_commit(bar_q_empty + st);
-        }
-        __syncwarp();
-        if (lane == 0) DTA_TRACE(3);
-        // dP^T of the next step needs R1 back from the drain warps
-        if (has_next) {
-          mbar_wait(bar_do_full, (it + 1) & 1);
-          mbar_wait(bar_r1_free, it & 1);
-          if (lane == 0) DTA_TRACE(4);
+        issue_dp();
+        uint32_t st = 0;
+        for (int it = 0; it < n_iter; ++it) {
+          const bool has_next = it + 1 < n_iter;
+          const uint32_t not_first = it > 0 ? 1u : 0u;
+          // dQ^T = K^T dS^T (first, so the drain overlaps dK), dK += dS^T Q
+          mbar_wait(bar_ds_full, it & 1);
+          if (lane == 0) DTA_TRACE(2);
           tc_fence_after();
-          issue_dp();
-          if (lane == 0) DTA_TRACE(5);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) umma_ss_lo(R1, nK + DTA_NOFF(kk), nDS + DTA_NOFF(kk), idesc_nn, kk > 0);
+            umma_commit(bar_dq_full);
+            const uint32_t b = nQ + st * kStage;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss_lo(RdK, kDS + DTA_KOFF(kk), b + DTA_NOFF(kk), idesc_kn, (kk > 0) ? 1u : not_first);
+            umma_commit(bar_q_empty + st);         // S^T(it) (warp A) retired long ago: dK(it) depends on it through P^T / dS^T
+          }
+          __syncwarp();
+          if (lane == 0) DTA_TRACE(3);
+          // dP^T of the next step needs R1 back from the drain warps
+          if (has_next) {
+            mbar_wait(bar_do_full, (it + 1) & 1);
+            mbar_wait(bar_r1_free, it & 1);
+            if (lane == 0) DTA_TRACE(4);
+            tc_fence_after();
+            issue_dp();
+            if (lane == 0) DTA_TRACE(5);
+          }
+          st = st + 1 == kQStages ? 0u : st + 1;
         }
-        st = nst;
-        stph = nph;
       }
-      if (elect_one()) umma_commit(bar_dkv_full);
+      if (elect_one()) umma_commit(bar_dkv_full);     // one arrival per issuing warp
       __syncwarp();
     }
   } else if (warp >= 12) {
@@ -361,26 +378,29 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_fence_after();
       float pr[64];
       tmem_ld_x32(R0 + lane_addr + ch * 64, reinterpret_cast<uint32_t*>(pr));
-      tmem_ld_x32(R0 + lane_addr + ch * 64 + 32, reinterpret_cast<uint32_t*>(pr) + 32);
       tmem_ld_wait();
+      tmem_ld_x32(R0 + lane_addr + ch * 64 + 32, reinterpret_cast<uint32_t*>(pr) + 32);   // in flight under the first half
       // The MMA already added the per-query exponent offset (broadcast k-step), so
       // pr = scale * P^T = 2^(S'^T * scale_log2) with no per-column operand: the 64 lse values every thread used
-      // to pull through LDS (4 wavefronts per LDS.128, broadcast or not) were ~1k of the ~5k data-pipe cycles of
-      // a step, on a pipe the UMMA operand fetch saturates by itself.  The 1/scale is undone once, in the dV
-      // epilogue, so that dS^T = pr * dP'^T needs no further multiply.  Two code copies: tiles the ancestor
-      // mask leaves untouched pay nothing for it.
-      if (!partial) {
+      // to pull through LDS (4 wavefronts per LDS.128, broadcast or not) were ~1k data-pipe cycles per step.
+      // The 1/scale is undone once, in the dV epilogue, so that dS^T = pr * dP'^T needs no further multiply.
+      // Two code copies: tiles the ancestor mask leaves untouched pay nothing for it.
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          const float x = pr[c] * p.scale_log2;
-          pr[c] = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
-        }
-      } else {
+      for (int hf = 0; hf < 2; ++hf) {
+        if (hf == 1) tmem_ld_wait();
+        if (!partial) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          const float x = pr[c] * p.scale_log2;
-          const float v = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
-          pr[c] = (c >= vis_lo && c < vis_hi) ? v : 0.f;
+          for (int c = hf * 32; c < hf * 32 + 32; ++c) {
+            const float x = pr[c] * p.scale_log2;
+            pr[c] = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
+          }
+        } else {
+#pragma unroll
+          for (int c = hf * 32; c < hf * 32 + 32; ++c) {
+            const float x = pr[c] * p.scale_log2;
+            const float v = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
+            pr[c] = (c >= vis_lo && c < vis_hi) ? v : 0.f;
+          }
         }
       }
       {
@@ -414,7 +434,8 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           dsp[16 + i] = pack_bf16x2(pr[32 + 2 * i] * dp1[2 * i], pr[32 + 2 * i + 1] * dp1[2 * i + 1]);
       }
       tc_fence_before();                   // our R1 reads are done before the arrive below
-      if (it > 0) mbar_wait(bar_ds_empty, (it - 1) & 1);
+      // sdS is free: dK(it-1), its last reader, was issued by the same warp before dP^T(it), and dp_full(it) -- which
+      // this warp has already observed -- is a tcgen05.commit covering every earlier MMA of that warp.
       uint8_t* dst = sdS + ch * kHalf;
 #pragma unroll
       for (int chunk = 0; chunk < 8; ++chunk) {
@@ -493,12 +514,12 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // hands them to the TMA unit as ONE tensor reduce-add; no other warp is involved, so the only
         // synchronisation is __syncwarp + the bulk-group read fence of the issuing lane.  512 reds per step and
         // SM (one 128-byte red per ~5 LSU cycles, all step long) become 512 single-wavefront stores + 32 TMA ops.
-        float* stage = reinterpret_cast<float*>(smem + BwdSmem::dq_stage) + (warp & 3) * (2 * kDqRows * 32);
+        float* stage = reinterpret_cast<float*>(smem + BwdSmem::dq_stage) + (warp & 3) * (kDqBufs * kDqRows * 32);
         const int c0 = head * kT + ((warp & 3) << 5);
 #pragma unroll
         for (int ck = 0; ck < kT / kDqRows; ++ck) {
-          float* buf = stage + (ck & 1) * (kDqRows * 32);
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer of chunk ck-2 is free
+          float* buf = stage + ((it * (kT / kDqRows) + ck) % kDqBufs) * (kDqRows * 32);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kDqBufs - 1) : "memory");   // oldest buffer is free
           __syncwarp();
 #pragma unroll
           for (int r = 0; r < kDqRows; ++r) buf[r * 32 + lane] = acc[ck * kDqRows + r];
