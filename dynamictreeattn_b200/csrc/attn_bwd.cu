@@ -590,30 +590,46 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
                                                          int64_t head_stride, const float* __restrict__ lse2,
                                                          float lshift, float inv_scale_log2,
                                                          uint4* __restrict__ aug_lse, uint4* __restrict__ aug_delta) {
-  const int lane = threadIdx.x & 31;
+  // half-warp per (q, h) row, 16 bytes per lane and tensor, four row pairs loaded before the first is reduced
+  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   const int64_t n_rows = static_cast<int64_t>(n_pad) * n_heads;
-  for (int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; w < n_rows;
-       w += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) {
-    const int q = static_cast<int>(w / n_heads), h = static_cast<int>(w % n_heads);
-    float acc = 0.f;
-    if (q < n_nodes) {
-      const int64_t off = q * row_stride + h * head_stride + lane * 4;
-      const uint2 a = *reinterpret_cast<const uint2*>(out + off);
-      const uint2 b = *reinterpret_cast<const uint2*>(dout + off);
-      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t w0 = ((blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5) * 8; w0 < n_rows; w0 += n_warps * 8) {
+    uint4 a[4], b[4];
+    float l2[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+    for (int u = 0; u < 4; ++u) {
+      const int64_t w = w0 + 2 * u + half;
+      const int q = static_cast<int>(w / n_heads), h = static_cast<int>(w % n_heads);
+      a[u] = b[u] = make_uint4(0u, 0u, 0u, 0u);
+      l2[u] = 0.f;
+      if (w < n_rows && q < n_nodes) {
+        const int64_t off = q * row_stride + h * head_stride + hl * 8;
+        a[u] = __ldg(reinterpret_cast<const uint4*>(out + off));
+        b[u] = __ldg(reinterpret_cast<const uint4*>(dout + off));
+        if (hl == 0) l2[u] = __ldg(lse2 + static_cast<int64_t>(h) * n_pad + q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t w = w0 + 2 * u + half;
+      const int q = static_cast<int>(w / n_heads), h = static_cast<int>(w % n_heads);
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a[u]);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b[u]);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
         const float2 x = __bfloat1622float2(a2[i]), y = __bfloat1622float2(b2[i]);
         acc = fmaf(x.x, y.x, acc);
         acc = fmaf(x.y, y.y, acc);
       }
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      const int64_t o = static_cast<int64_t>(h) * n_pad + q;
-      aug_delta[o] = split3_bf16(-acc);
-      aug_lse[o] = split3_bf16(q < n_nodes ? (lshift - lse2[o]) * inv_scale_log2 : 0.f);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (hl == 0 && w < n_rows) {
+        const int64_t o = static_cast<int64_t>(h) * n_pad + q;
+        aug_delta[o] = split3_bf16(-acc);
+        aug_lse[o] = split3_bf16(q < n_nodes ? (lshift - l2[u]) * inv_scale_log2 : 0.f);
+      }
     }
   }
 }
@@ -687,7 +703,7 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
 
   const int64_t n_rows = static_cast<int64_t>(sh->n_pad) * sh->n_q_heads;
   {
-    int64_t grid = (n_rows * 32 + 255) / 256;
+    int64_t grid = ((n_rows + 7) / 8 * 32 + 255) / 256;
     const int64_t cap = 16 * static_cast<int64_t>(sm_count());
     if (grid > cap) grid = cap;
     attn_delta_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(

@@ -321,6 +321,68 @@ __device__ __forceinline__ constexpr bool exp2_slot_on_fma(int e) {
   return ((e & 7) * kOf8) / 8 != (((e & 7) + 1) * kOf8) / 8;
 }
 
+// ----------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 process two fp32 lanes per issue slot on the FMA
+// pipe, whose 3-register forms otherwise issue every other cycle).  A pair lives in one 64-bit register.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_bcast(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add_rm(uint64_t a, uint64_t b) {   // round toward -inf
+  uint64_t d;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// poly_exp2 on a pair: same arithmetic, element for element, as the scalar version above
+__device__ __forceinline__ uint64_t poly_exp2_x2(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t fl = f2_add_rm(x, f2_bcast(12582912.f));
+  const uint64_t f = f2_sub(x, f2_add(fl, f2_bcast(-12582912.f)));
+  uint64_t p = f2_fma(f, f2_bcast(0.077119089663f), f2_bcast(0.227564394474f));
+  p = f2_fma(p, f, f2_bcast(0.695146143436f));
+  p = f2_fma(p, f, f2_bcast(1.0f));
+  float p0, p1, f0, f1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(fl, f0, f1);
+  return f2_pack(__int_as_float(__float_as_int(p0) + (__float_as_int(f0) << 23)),
+                 __int_as_float(__float_as_int(p1) + (__float_as_int(f1) << 23)));
+}
+// Of every 4 PAIRS of exponentials, kOf8 / 2 go to the FMA pipes (pair-granular version of exp2_slot_on_fma)
+template <int kOf8>
+__device__ __forceinline__ constexpr bool exp2_pair_on_fma(int pair) {
+  return ((pair & 3) * (kOf8 / 2)) / 4 != (((pair & 3) + 1) * (kOf8 / 2)) / 4;
+}
+
 // 128-byte swizzle: byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a [rows][128 B] tile
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
   return row * 128u + ((chunk ^ (row & 7u)) << 4);

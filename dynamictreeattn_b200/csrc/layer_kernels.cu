@@ -49,6 +49,18 @@ __device__ __forceinline__ float block_sum(float v, float* smem) {
 //   s = bf16(x + res)   (written to `sum_out` when res != NULL; HF adds the residual in bf16)
 //   y = bf16( s * rstd * w ),  rstd = rsqrt(mean(s^2) + eps)
 // ------------------------------------------------------------------------------------
+// Both kernels are latency-bound per row (load -> block reduction -> store), so the loads of the CTA's NEXT row are
+// issued before the reduction of the current one: two rows per CTA in flight, 8 CTAs per SM.
+__device__ __forceinline__ void cvt8(const uint4 v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
 __global__ void __launch_bounds__(1024) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                            const __nv_bfloat16* __restrict__ res,
                                                            const __nv_bfloat16* __restrict__ w, int64_t n_rows, int H,
@@ -59,12 +71,25 @@ __global__ void __launch_bounds__(1024) rmsnorm_fwd_kernel(const __nv_bfloat16* 
   const int c = threadIdx.x * 8;
   float wf[8];
   ld8(w + c, wf);
-  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+  const bool has_res = res != nullptr;
+  int64_t row = blockIdx.x;
+  uint4 xr = make_uint4(0, 0, 0, 0), rr = make_uint4(0, 0, 0, 0);
+  if (row < n_rows) {
+    xr = ldg16(x + row * H + c);
+    if (has_res) rr = ldg16(res + row * H + c);
+  }
+  while (row < n_rows) {
+    const int64_t next = row + gridDim.x;
+    uint4 xn = make_uint4(0, 0, 0, 0), rn = make_uint4(0, 0, 0, 0);
+    if (next < n_rows) {
+      xn = ldg16(x + next * H + c);
+      if (has_res) rn = ldg16(res + next * H + c);
+    }
     float v[8];
-    ld8(x + row * H + c, v);
-    if (res != nullptr) {
+    cvt8(xr, v);
+    if (has_res) {
       float r[8];
-      ld8(res + row * H + c, r);
+      cvt8(rr, r);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = bf16_round(v[i] + r[i]);
       st8(sum_out + row * H + c, v);
@@ -78,6 +103,9 @@ __global__ void __launch_bounds__(1024) rmsnorm_fwd_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = v[i] * rstd * wf[i];
     st8(y + row * H + c, v);
+    xr = xn;
+    rr = rn;
+    row = next;
   }
 }
 
@@ -95,11 +123,29 @@ __global__ void __launch_bounds__(1024) rmsnorm_bwd_kernel(const __nv_bfloat16* 
   ld8(w + c, wf);
 #pragma unroll
   for (int i = 0; i < 8; ++i) dwacc[i] = 0.f;
-  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+  const bool has_res = dres != nullptr;
+  int64_t row = blockIdx.x;
+  uint4 gr = make_uint4(0, 0, 0, 0), xr = gr, rr = gr;
+  float rstd = 0.f;
+  if (row < n_rows) {
+    gr = ldg16(dy + row * H + c);
+    xr = ldg16(x + row * H + c);
+    if (has_res) rr = ldg16(dres + row * H + c);
+    rstd = __ldg(rstd_in + row);
+  }
+  while (row < n_rows) {
+    const int64_t next = row + gridDim.x;
+    uint4 gn = make_uint4(0, 0, 0, 0), xn = gn, rn = gn;
+    float rstd_n = 0.f;
+    if (next < n_rows) {
+      gn = ldg16(dy + next * H + c);
+      xn = ldg16(x + next * H + c);
+      if (has_res) rn = ldg16(dres + next * H + c);
+      rstd_n = __ldg(rstd_in + next);
+    }
     float g[8], xv[8];
-    ld8(dy + row * H + c, g);
-    ld8(x + row * H + c, xv);
-    const float rstd = rstd_in[row];
+    cvt8(gr, g);
+    cvt8(xr, xv);
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -112,16 +158,91 @@ __global__ void __launch_bounds__(1024) rmsnorm_bwd_kernel(const __nv_bfloat16* 
     float out[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) out[i] = rstd * (g[i] - xv[i] * dot);
-    if (dres != nullptr) {
+    if (has_res) {
       float r[8];
-      ld8(dres + row * H + c, r);
+      cvt8(rr, r);
 #pragma unroll
       for (int i = 0; i < 8; ++i) out[i] += r[i];
     }
     st8(dx + row * H + c, out);
+    gr = gn;
+    xr = xn;
+    rr = rn;
+    rstd = rstd_n;
+    row = next;
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) atomicAdd(dw + c + i, dwacc[i]);
+}
+
+// Warp-per-row backward for hidden <= 1024 (kVec = hidden / 256 16-byte vectors per lane and tensor): no block-wide
+// reduction on the row's critical path, every load of a row issued at once, 16-24 rows in flight per SM.
+// dw: per-lane fp32 partials -> shared-memory reduction over the CTA's warps -> one global atomic per column and CTA.
+template <int kVec>
+__global__ void __launch_bounds__(256, 2) rmsnorm_bwd_warp_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                              const __nv_bfloat16* __restrict__ x,
+                                                              const __nv_bfloat16* __restrict__ w,
+                                                              const float* __restrict__ rstd_in,
+                                                              const __nv_bfloat16* __restrict__ dres, int64_t n_rows,
+                                                              __nv_bfloat16* __restrict__ dx, float* __restrict__ dw) {
+  constexpr int H = kVec * 256;
+  __shared__ float sdw[H];
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) sdw[i] = 0.f;
+  float dwacc[kVec][8];
+#pragma unroll
+  for (int v = 0; v < kVec; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dwacc[v][i] = 0.f;
+  const bool has_res = dres != nullptr;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
+    uint4 gr[kVec], xr[kVec], rr[kVec];
+#pragma unroll
+    for (int v = 0; v < kVec; ++v) {
+      const int64_t off = row * H + v * 256 + lane * 8;
+      gr[v] = ldg16(dy + off);
+      xr[v] = ldg16(x + off);
+      rr[v] = has_res ? ldg16(dres + off) : make_uint4(0, 0, 0, 0);
+    }
+    const float rstd = __ldg(rstd_in + row);
+    float dot = 0.f;
+    // two passes over the raw registers (the bf16 -> fp32 unpack is two ALU ops) instead of keeping fp32 copies live
+#pragma unroll
+    for (int v = 0; v < kVec; ++v) {
+      float wf[8], g[8], xv[8];
+      ld8(w + v * 256 + lane * 8, wf);
+      cvt8(gr[v], g);
+      cvt8(xr[v], xv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = xv[i] * rstd;
+        dwacc[v][i] = fmaf(g[i], xh, dwacc[v][i]);
+        dot = fmaf(g[i] * wf[i], xh, dot);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    dot *= (1.f / H);
+#pragma unroll
+    for (int v = 0; v < kVec; ++v) {
+      float wf[8], g[8], xv[8], r[8], out[8];
+      ld8(w + v * 256 + lane * 8, wf);
+      cvt8(gr[v], g);
+      cvt8(xr[v], xv);
+      cvt8(rr[v], r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[i] = rstd * (g[i] * wf[i] - xv[i] * rstd * dot) + r[i];
+      st8(dx + row * H + v * 256 + lane * 8, out);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < kVec; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sdw[v * 256 + lane * 8 + i], dwacc[v][i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(dw + i, sdw[i]);
 }
 
 // ------------------------------------------------------------------------------------
@@ -262,6 +383,157 @@ __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(const QkBwdArgs a)
 }
 
 // ------------------------------------------------------------------------------------
+// 16-byte versions of the two kernels above (strides multiples of 8 elements, 16-byte aligned bases): one warp per
+// NODE, one half-warp per head row (lane hl of the half owns elements 8hl..8hl+7, its rotate_half partner is lane
+// hl ^ 8), four head pairs loaded before the first is reduced.  The node's depth / cos / sin are fetched once for
+// all of its heads, and 8 rows x 256 B are in flight per warp instead of one.
+// ------------------------------------------------------------------------------------
+static constexpr int kQkUnroll = 4;   // head PAIRS in flight per warp
+
+__global__ void __launch_bounds__(256) qknorm_rope_fwd_v8_kernel(const QkArgs a) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+  const int heads = a.hq + a.hkv;
+  float wq[8], wk[8];
+  ld8(a.wq + hl * 8, wq);
+  ld8(a.wk + hl * 8, wk);
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t n = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; n < a.n_rows; n += n_warps) {
+    const float* cs_row = a.cos_sin + static_cast<int64_t>(__ldg(a.depth + n)) * 128 + (hl & 7) * 8;
+    float cs[8], sn[8];
+    *reinterpret_cast<float4*>(cs) = __ldg(reinterpret_cast<const float4*>(cs_row));
+    *reinterpret_cast<float4*>(cs + 4) = __ldg(reinterpret_cast<const float4*>(cs_row + 4));
+    *reinterpret_cast<float4*>(sn) = __ldg(reinterpret_cast<const float4*>(cs_row + 64));
+    *reinterpret_cast<float4*>(sn + 4) = __ldg(reinterpret_cast<const float4*>(cs_row + 68));
+    if (hl < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sn[j] = -sn[j];          // first half of the head: x c - partner s
+    }
+    for (int h0 = 0; h0 < heads; h0 += 2 * kQkUnroll) {
+      uint4 raw[kQkUnroll];
+#pragma unroll
+      for (int u = 0; u < kQkUnroll; ++u) {
+        const int h = h0 + 2 * u + half;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (h < heads) {
+          const __nv_bfloat16* src = h < a.hq ? a.q + n * a.q_row + h * a.q_head : a.k + n * a.k_row + (h - a.hq) * a.k_head;
+          raw[u] = ldg16(src + hl * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kQkUnroll; ++u) {
+        const int h = h0 + 2 * u + half;
+        const bool is_q = h < a.hq;
+        float v[8];
+        cvt8(raw[u], v);
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float rstd = rsqrtf(ss * (1.f / 128.f) + a.eps);
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = v[j] * rstd * (is_q ? wq[j] : wk[j]);
+          const float partner = __shfl_xor_sync(0xffffffffu, xh, 8);
+          out[j] = fmaf(partner, sn[j], xh * cs[j]);
+        }
+        if (h < heads) {
+          if (hl == 0) a.rstd[n * heads + h] = rstd;
+          __nv_bfloat16* dst = is_q ? a.q_out + (n * a.hq + h) * 128 : a.k_out + (n * a.hkv + (h - a.hq)) * 128;
+          st8(dst + hl * 8, out);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) qknorm_rope_bwd_v8_kernel(const QkBwdArgs a) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+  const int heads = a.hq + a.hkv;
+  float wq[8], wk[8], accq[8], acck[8];
+  ld8(a.wq + hl * 8, wq);
+  ld8(a.wk + hl * 8, wk);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) accq[j] = acck[j] = 0.f;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t n = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; n < a.n_rows; n += n_warps) {
+    const float* cs_row = a.cos_sin + static_cast<int64_t>(__ldg(a.depth + n)) * 128 + (hl & 7) * 8;
+    float cs[8], sn[8];
+    *reinterpret_cast<float4*>(cs) = __ldg(reinterpret_cast<const float4*>(cs_row));
+    *reinterpret_cast<float4*>(cs + 4) = __ldg(reinterpret_cast<const float4*>(cs_row + 4));
+    *reinterpret_cast<float4*>(sn) = __ldg(reinterpret_cast<const float4*>(cs_row + 64));
+    *reinterpret_cast<float4*>(sn + 4) = __ldg(reinterpret_cast<const float4*>(cs_row + 68));
+    if (hl >= 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sn[j] = -sn[j];          // transpose of the rotation: second half gets - do[i] s
+    }
+    for (int h0 = 0; h0 < heads; h0 += 2 * kQkUnroll) {
+      uint4 graw[kQkUnroll], xraw[kQkUnroll];
+      float rstd_u[kQkUnroll];
+#pragma unroll
+      for (int u = 0; u < kQkUnroll; ++u) {
+        const int h = h0 + 2 * u + half;
+        graw[u] = xraw[u] = make_uint4(0, 0, 0, 0);
+        rstd_u[u] = 0.f;
+        if (h < heads) {
+          const bool is_q = h < a.hq;
+          const int hh = is_q ? h : h - a.hq;
+          graw[u] = ldg16((is_q ? a.dq_out + (n * a.hq + hh) * 128 : a.dk_out + (n * a.hkv + hh) * 128) + hl * 8);
+          xraw[u] = ldg16((is_q ? a.q + n * a.q_row + hh * a.q_head : a.k + n * a.k_row + hh * a.k_head) + hl * 8);
+          rstd_u[u] = __ldg(a.rstd + n * heads + h);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kQkUnroll; ++u) {
+        const int h = h0 + 2 * u + half;
+        const bool is_q = h < a.hq;
+        const int hh = is_q ? h : h - a.hq;
+        float go[8], xh[8], g[8];
+        cvt8(graw[u], go);
+        cvt8(xraw[u], xh);
+        const float rstd = rstd_u[u];
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float partner = __shfl_xor_sync(0xffffffffu, go[j], 8);
+          // d xh[i] = do[i] c + do[i+64] s ; d xh[i+64] = do[i+64] c - do[i] s
+          const float dxh = fmaf(partner, sn[j], go[j] * cs[j]);
+          xh[j] *= rstd;
+          if (is_q) accq[j] = fmaf(dxh, xh[j], accq[j]); else acck[j] = fmaf(dxh, xh[j], acck[j]);
+          g[j] = dxh * (is_q ? wq[j] : wk[j]);
+          dot = fmaf(g[j], xh[j], dot);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        dot *= (1.f / 128.f);
+        if (h < heads) {
+          float out[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) out[j] = rstd * (g[j] - xh[j] * dot);
+          __nv_bfloat16* dst = is_q ? a.dq + n * a.dq_row + hh * a.dq_head : a.dk + n * a.dk_row + hh * a.dk_head;
+          st8(dst + hl * 8, out);
+        }
+      }
+    }
+  }
+  // weight gradients: reduce over the CTA's warps in shared memory, one atomic per column per CTA
+  __shared__ float sq[128], sk[128];
+  if (threadIdx.x < 128) { sq[threadIdx.x] = 0.f; sk[threadIdx.x] = 0.f; }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sq[hl * 8 + j], accq[j]);
+    atomicAdd(&sk[hl * 8 + j], acck[j]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    atomicAdd(a.dwq + threadIdx.x, sq[threadIdx.x]);
+    atomicAdd(a.dwk + threadIdx.x, sk[threadIdx.x]);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // SwiGLU: m = silu(g) * u ;  dg = dm * u * sig(g) * (1 + g * (1 - sig(g))), du = dm * silu(g)
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ g,
@@ -337,11 +609,27 @@ int dta_rmsnorm_bwd(const void* dy, const void* x, const void* weight, const flo
   DTA_REQUIRE(dy && x && weight && rstd && dx && dweight, "NULL pointer argument");
   DTA_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(weight) && aligned16(dx) && aligned16(dresidual),
               "tensors must be 16-byte aligned");
-  const int64_t cap = 4 * static_cast<int64_t>(sm_count());
-  rmsnorm_bwd_kernel<<<static_cast<int>(n_rows < cap ? n_rows : cap), hidden / 8, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
-      static_cast<const __nv_bfloat16*>(weight), rstd, static_cast<const __nv_bfloat16*>(dresidual), n_rows, hidden,
-      static_cast<__nv_bfloat16*>(dx), dweight);
+  const __nv_bfloat16* dy_ = static_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* x_ = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* w_ = static_cast<const __nv_bfloat16*>(weight);
+  const __nv_bfloat16* dr_ = static_cast<const __nv_bfloat16*>(dresidual);
+  __nv_bfloat16* dx_ = static_cast<__nv_bfloat16*>(dx);
+  if (hidden <= 1024) {
+    int64_t grid = (n_rows + 7) / 8;                      // 8 warps = 8 rows per CTA iteration
+    const int64_t cap2 = 2 * static_cast<int64_t>(sm_count());  // 2 resident CTAs per SM (128 registers)
+    if (grid > cap2) grid = cap2;
+    const int g = static_cast<int>(grid);
+    switch (hidden / 256) {
+      case 1: rmsnorm_bwd_warp_kernel<1><<<g, 256, 0, stream>>>(dy_, x_, w_, rstd, dr_, n_rows, dx_, dweight); break;
+      case 2: rmsnorm_bwd_warp_kernel<2><<<g, 256, 0, stream>>>(dy_, x_, w_, rstd, dr_, n_rows, dx_, dweight); break;
+      case 3: rmsnorm_bwd_warp_kernel<3><<<g, 256, 0, stream>>>(dy_, x_, w_, rstd, dr_, n_rows, dx_, dweight); break;
+      default: rmsnorm_bwd_warp_kernel<4><<<g, 256, 0, stream>>>(dy_, x_, w_, rstd, dr_, n_rows, dx_, dweight); break;
+    }
+  } else {
+    const int64_t cap = 8 * static_cast<int64_t>(sm_count());
+    rmsnorm_bwd_kernel<<<static_cast<int>(n_rows < cap ? n_rows : cap), hidden / 8, 0, stream>>>(dy_, x_, w_, rstd, dr_,
+                                                                                                  n_rows, hidden, dx_, dweight);
+  }
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
 }
@@ -361,7 +649,13 @@ int dta_qknorm_rope_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stri
            static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(k_out),
            static_cast<const __nv_bfloat16*>(wq), static_cast<const __nv_bfloat16*>(wk), depth, cos_sin, rstd,
            n_rows, n_q_heads, n_kv_heads, eps};
-  qknorm_rope_fwd_kernel<<<elem_grid(n_rows * (n_q_heads + n_kv_heads) * 32, 256), 256, 0, stream>>>(a);
+  const bool v8 = q_row_stride % 8 == 0 && q_head_stride % 8 == 0 && k_row_stride % 8 == 0 && k_head_stride % 8 == 0 &&
+                  aligned16(q) && aligned16(k) && aligned16(q_out) && aligned16(k_out) && aligned16(wq) && aligned16(wk) &&
+                  aligned16(cos_sin);
+  if (v8)
+    qknorm_rope_fwd_v8_kernel<<<elem_grid(n_rows * 32, 256), 256, 0, stream>>>(a);
+  else
+    qknorm_rope_fwd_kernel<<<elem_grid(n_rows * (n_q_heads + n_kv_heads) * 32, 256), 256, 0, stream>>>(a);
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
 }
@@ -383,10 +677,17 @@ int dta_qknorm_rope_bwd(const void* dq_out, const void* dk_out, const void* q, i
               static_cast<__nv_bfloat16*>(dk), dk_row_stride, dk_head_stride,
               static_cast<const __nv_bfloat16*>(wq), static_cast<const __nv_bfloat16*>(wk), depth, cos_sin, rstd,
               dwq, dwk, n_rows, n_q_heads, n_kv_heads};
-  const int64_t cap = 4 * static_cast<int64_t>(sm_count());
-  int64_t grid = (n_rows * (n_q_heads + n_kv_heads) * 32 + 255) / 256;
+  const bool v8 = q_row_stride % 8 == 0 && q_head_stride % 8 == 0 && k_row_stride % 8 == 0 && k_head_stride % 8 == 0 &&
+                  dq_row_stride % 8 == 0 && dq_head_stride % 8 == 0 && dk_row_stride % 8 == 0 && dk_head_stride % 8 == 0 &&
+                  aligned16(q) && aligned16(k) && aligned16(dq) && aligned16(dk) && aligned16(dq_out) && aligned16(dk_out) &&
+                  aligned16(wq) && aligned16(wk) && aligned16(cos_sin);
+  const int64_t cap = 8 * static_cast<int64_t>(sm_count());
+  int64_t grid = ((v8 ? n_rows : n_rows * (n_q_heads + n_kv_heads)) * 32 + 255) / 256;
   if (grid > cap) grid = cap;
-  qknorm_rope_bwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  if (v8)
+    qknorm_rope_bwd_v8_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  else
+    qknorm_rope_bwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(a);
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
 }

@@ -19,7 +19,7 @@ from . import _cabi
 from .attention import tree_attention
 from .linearize import TrieLayout
 
-__all__ = ["add_rmsnorm", "qknorm_rope", "swiglu", "fused_trunk_forward", "supports_fused_trunk", "rope_table"]
+__all__ = ["add_rmsnorm", "qknorm_rope", "swiglu", "multi_linear", "fused_trunk_forward", "supports_fused_trunk", "rope_table"]
 
 
 def _st(t: torch.Tensor) -> int:
@@ -140,6 +140,41 @@ def swiglu(gate, up):
     return _SwiGLU.apply(gate, up)
 
 
+class _MultiLinear(torch.autograd.Function):
+    """(x W_0^T, x W_1^T, ...) for bias-free projections that share their input (q/k/v, gate/up).
+
+    Same cuBLAS GEMMs as separate ``F.linear`` calls; the point is the backward: d x is accumulated inside the
+    GEMM epilogues (``addmm_`` with beta = 1, fp32 accumulation, one bf16 rounding) instead of by one elementwise
+    add kernel per extra consumer, which autograd inserts when the same tensor feeds several ``F.linear``s.
+    """
+
+    @staticmethod
+    def forward(ctx, x, *weights):
+        ctx.save_for_backward(x, *weights)
+        return tuple(torch.mm(x, w.t()) for w in weights)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, *weights = ctx.saved_tensors
+        dx = None
+        if ctx.needs_input_grad[0]:
+            for g, w in zip(grads, weights):
+                if g is None:
+                    continue
+                if dx is None:
+                    dx = torch.mm(g, w)
+                else:
+                    dx.addmm_(g, w)
+        dws = []
+        for i, g in enumerate(grads):
+            dws.append(torch.mm(g.t(), x) if g is not None and ctx.needs_input_grad[1 + i] else None)
+        return (dx, *dws)
+
+
+def multi_linear(x, *weights):
+    return _MultiLinear.apply(x, *weights)
+
+
 # ---------------------------------------------------------------------------------------
 # trunk
 # ---------------------------------------------------------------------------------------
@@ -185,13 +220,13 @@ def fused_trunk_forward(model, layout: TrieLayout) -> torch.Tensor:
     for layer in base.layers:
         at, mlp = layer.self_attn, layer.mlp
         h, residual = add_rmsnorm(x, residual, layer.input_layernorm.weight, eps)
-        q = F.linear(h, at.q_proj.weight).view(n, hq, d)
-        k = F.linear(h, at.k_proj.weight).view(n, hkv, d)
-        v = F.linear(h, at.v_proj.weight).view(n, hkv, d)
+        q, k, v = multi_linear(h, at.q_proj.weight, at.k_proj.weight, at.v_proj.weight)
+        q, k, v = q.view(n, hq, d), k.view(n, hkv, d), v.view(n, hkv, d)
         q, k = qknorm_rope(q, k, at.q_norm.weight, at.k_norm.weight, depth, table, eps)
         a = tree_attention(q, k, v, layout, at.scaling)
         o = F.linear(a.view(n, hq * d), at.o_proj.weight)
         h, residual = add_rmsnorm(o, residual, layer.post_attention_layernorm.weight, eps)
-        x = F.linear(swiglu(F.linear(h, mlp.gate_proj.weight), F.linear(h, mlp.up_proj.weight)), mlp.down_proj.weight)
+        gate, up = multi_linear(h, mlp.gate_proj.weight, mlp.up_proj.weight)
+        x = F.linear(swiglu(gate, up), mlp.down_proj.weight)
     h, _ = add_rmsnorm(x, residual, base.norm.weight, eps)
     return h

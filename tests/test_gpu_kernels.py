@@ -308,11 +308,14 @@ def test_add_rmsnorm_fwd_bwd(hidden):
     assert s2 is x2 and _rel(y2, _hf_rmsnorm(x2.detach(), w.detach(), 1e-6)) < 4e-3
 
 
-def test_qknorm_rope_fwd_bwd():
+@pytest.mark.parametrize("hq,hkv,pad", [(4, 2, 0), (16, 8, 0), (3, 2, 0), (4, 2, 4)])
+def test_qknorm_rope_fwd_bwd(hq, hkv, pad):
+    """pad = 4 shifts the q/k views to 8-byte alignment only: the 8-byte fallback kernels instead of the 16-byte ones."""
     from dynamictreeattn_b200.fused_layers import qknorm_rope
     torch.manual_seed(0)
-    n, hq, hkv, d = 500, 4, 2, 128
-    buf = torch.randn(n, (hq + hkv) * d, device="cuda").bfloat16().requires_grad_(True)
+    n, d = 500, 128
+    raw = torch.randn(n, (hq + hkv) * d + 2 * pad, device="cuda").bfloat16().requires_grad_(True)
+    buf = raw[:, pad:pad + (hq + hkv) * d]
     wq = (1 + 0.1 * torch.randn(d, device="cuda")).bfloat16().requires_grad_(True)
     wk = (1 + 0.1 * torch.randn(d, device="cuda")).bfloat16().requires_grad_(True)
     depth = torch.randint(0, 9000, (n,), device="cuda", dtype=torch.int32)
@@ -338,7 +341,29 @@ def test_qknorm_rope_fwd_bwd():
     kr = ref(bufr[:, hq * d:].view(n, hkv, d), wkr)
     torch.autograd.backward([qr, kr], [gq.float(), gk.float()])
     assert _rel(qo, qr) < 4e-3 and _rel(ko, kr) < 4e-3
-    assert _rel(buf.grad, bufr.grad) < 6e-3 and _rel(wq.grad, wqr.grad) < 6e-3 and _rel(wk.grad, wkr.grad) < 6e-3
+    got = raw.grad[:, pad:pad + (hq + hkv) * d]
+    assert _rel(got, bufr.grad) < 6e-3 and _rel(wq.grad, wqr.grad) < 6e-3 and _rel(wk.grad, wkr.grad) < 6e-3
+
+
+def test_multi_linear_matches_separate_linears():
+    import torch.nn.functional as F
+    from dynamictreeattn_b200.fused_layers import multi_linear
+    torch.manual_seed(0)
+    n, hin = 300, 256
+    x = torch.randn(n, hin, device="cuda").bfloat16().requires_grad_(True)
+    ws = [torch.randn(o, hin, device="cuda").bfloat16().mul_(0.05).requires_grad_(True) for o in (512, 128, 128)]
+    gs = [torch.randn(n, o, device="cuda").bfloat16() for o in (512, 128, 128)]
+    ys = multi_linear(x, *ws)
+    torch.autograd.backward(list(ys), gs)
+    xr = x.detach().float().requires_grad_(True)
+    wr = [w.detach().float().requires_grad_(True) for w in ws]
+    yr = [F.linear(xr, w) for w in wr]
+    torch.autograd.backward(yr, [g.float() for g in gs])
+    for y, r in zip(ys, yr):
+        assert _rel(y, r) < 4e-3
+    assert _rel(x.grad, xr.grad) < 4e-3
+    for w, r in zip(ws, wr):
+        assert _rel(w.grad, r.grad) < 4e-3
 
 
 def test_swiglu_fwd_bwd():
