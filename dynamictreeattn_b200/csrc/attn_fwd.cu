@@ -41,7 +41,6 @@ static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kLn2 = 0.6931471805599453f;
 static constexpr float kRescaleThreshold = 8.0f;      // log2 units
 static constexpr int kDefaultFwdPoly = 2;             // of every 8 exponentials, on the FMA pipes
-static constexpr int kDefaultFwdVariant = 2;          // see the kernel's kVariant
 
 struct FwdSmem {
   // offsets inside the 1024-aligned dynamic shared buffer
@@ -69,9 +68,7 @@ struct FwdParams {
 };
 
 // kPolyOf8: how many of every 8 exponentials run on the FMA pipes (poly_exp2) instead of MUFU
-// kVariant bit 0: row max as independent FMNMX3 chains; bit 1: packed fp32x2 exponent pass; bit 2: chunk-pipelined
-// TMEM load (max of chunk c under the load of chunk c+1)
-template <int kPolyOf8, int kVariant>
+template <int kPolyOf8>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const FwdParams p) {
@@ -261,72 +258,25 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_wait(bar_s_full + t, it & 1);
         tc_fence_after();
         float s[kBN];
-        float mx;
-        if constexpr ((kVariant & 4) == 0) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, reinterpret_cast<uint32_t*>(s) + c * 32);
-          tmem_ld_wait();
-          if (entry & 1) {  // boundary tile: per-element ancestor test
-            const int4* ends = reinterpret_cast<const int4*>(p.subtree_end + k0);
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, reinterpret_cast<uint32_t*>(s) + c * 32);
+        tmem_ld_wait();
+
+        if (entry & 1) {  // boundary tile: per-element ancestor test
+          const int4* ends = reinterpret_cast<const int4*>(p.subtree_end + k0);
 #pragma unroll
-            for (int c4 = 0; c4 < kBN / 4; ++c4) {
-              const int4 e = __ldg(ends + c4);
-              const int kb = k0 + c4 * 4;
-              if (!(kb + 0 <= q && q < e.x)) s[c4 * 4 + 0] = -INFINITY;
-              if (!(kb + 1 <= q && q < e.y)) s[c4 * 4 + 1] = -INFINITY;
-              if (!(kb + 2 <= q && q < e.z)) s[c4 * 4 + 2] = -INFINITY;
-              if (!(kb + 3 <= q && q < e.w)) s[c4 * 4 + 3] = -INFINITY;
-            }
+          for (int c4 = 0; c4 < kBN / 4; ++c4) {
+            const int4 e = __ldg(ends + c4);
+            const int kb = k0 + c4 * 4;
+            if (!(kb + 0 <= q && q < e.x)) s[c4 * 4 + 0] = -INFINITY;
+            if (!(kb + 1 <= q && q < e.y)) s[c4 * 4 + 1] = -INFINITY;
+            if (!(kb + 2 <= q && q < e.z)) s[c4 * 4 + 2] = -INFINITY;
+            if (!(kb + 3 <= q && q < e.w)) s[c4 * 4 + 3] = -INFINITY;
           }
-          if constexpr ((kVariant & 1) == 0) {
-            mx = s[0];
-#pragma unroll
-            for (int c = 1; c < kBN; ++c) mx = fmaxf(mx, s[c]);
-          } else {
-            // eight independent FMNMX3 chains instead of one 64-deep dependent chain
-            float m[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m[j] = fmaxf(s[2 * j], s[2 * j + 1]);
-#pragma unroll
-            for (int i = 16; i < kBN; i += 16)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaxf(m[j], s[i + 2 * j]), s[i + 2 * j + 1]);
-            mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-          }
-        } else {
-          // S arrives in four 32-column chunks; chunk c+1 is in flight while chunk c is masked and max-reduced
-          // (four independent FMNMX3 chains per chunk instead of one 64-deep dependent chain).
-          float mxc[4];
-          tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
-  #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            tmem_ld_wait();
-            if (c + 1 < 4) tmem_ld_x32(tS + (c + 1) * 32, reinterpret_cast<uint32_t*>(s) + (c + 1) * 32);
-            if (entry & 1) {  // boundary tile: per-element ancestor test
-              const int4* ends = reinterpret_cast<const int4*>(p.subtree_end + k0 + c * 32);
-  #pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4) {
-                const int4 e = __ldg(ends + c4);
-                const int kb = k0 + c * 32 + c4 * 4;
-                if (!(kb + 0 <= q && q < e.x)) s[c * 32 + c4 * 4 + 0] = -INFINITY;
-                if (!(kb + 1 <= q && q < e.y)) s[c * 32 + c4 * 4 + 1] = -INFINITY;
-                if (!(kb + 2 <= q && q < e.z)) s[c * 32 + c4 * 4 + 2] = -INFINITY;
-                if (!(kb + 3 <= q && q < e.w)) s[c * 32 + c4 * 4 + 3] = -INFINITY;
-              }
-            }
-            float m0 = fmaxf(s[c * 32 + 0], s[c * 32 + 1]), m1 = fmaxf(s[c * 32 + 2], s[c * 32 + 3]);
-            float m2a = fmaxf(s[c * 32 + 4], s[c * 32 + 5]), m3 = fmaxf(s[c * 32 + 6], s[c * 32 + 7]);
-  #pragma unroll
-            for (int i = 8; i < 32; i += 8) {
-              m0 = fmaxf(fmaxf(m0, s[c * 32 + i + 0]), s[c * 32 + i + 1]);
-              m1 = fmaxf(fmaxf(m1, s[c * 32 + i + 2]), s[c * 32 + i + 3]);
-              m2a = fmaxf(fmaxf(m2a, s[c * 32 + i + 4]), s[c * 32 + i + 5]);
-              m3 = fmaxf(fmaxf(m3, s[c * 32 + i + 6]), s[c * 32 + i + 7]);
-            }
-            mxc[c] = fmaxf(fmaxf(m0, m1), fmaxf(m2a, m3));
-          }
-          mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
         }
+        float mx = s[0];
+#pragma unroll
+        for (int c = 1; c < kBN; ++c) mx = fmaxf(mx, s[c]);
         mx *= p.scale_log2;
 
         // lazy rescale: keep the stale max unless the new one is > 2^8 larger
@@ -350,54 +300,35 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         l *= alpha;
         const float mref = (m2 == -INFINITY) ? 0.f : m2;
-        if constexpr ((kVariant & 2) == 0) {
-          float lsum = 0.f;
+        // exponentials two at a time: one FFMA2 scales and shifts a pair, the row sum is a pair of FADD2 chains,
+        // and the share of the exponentials that runs on the FMA pipes (poly_exp2_x2) is packed as well
+        const uint64_t scale2 = f2_bcast(p.scale_log2), nmref2 = f2_bcast(-mref);
+        uint64_t lsum_a = f2_bcast(0.f), lsum_b = f2_bcast(0.f);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t pk[16];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float x0 = fmaf(s[c * 32 + i], p.scale_log2, -mref);
-              const float x1 = fmaf(s[c * 32 + i + 1], p.scale_log2, -mref);
-              const float p0 = exp2_slot_on_fma<kPolyOf8>(i) ? poly_exp2(x0) : fast_exp2(x0);
-              const float p1 = exp2_slot_on_fma<kPolyOf8>(i + 1) ? poly_exp2(x1) : fast_exp2(x1);
-              lsum += p0 + p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t x2 = f2_fma(f2_pack(s[c * 32 + 2 * i], s[c * 32 + 2 * i + 1]), scale2, nmref2);
+            uint64_t p2;
+            if (exp2_pair_on_fma<kPolyOf8>(i)) {
+              p2 = poly_exp2_x2(x2);
+            } else {
+              float x0, x1;
+              f2_unpack(x2, x0, x1);
+              p2 = f2_pack(fast_exp2(x0), fast_exp2(x1));
             }
-            tmem_st_x16(tS + c * 16, pk);
+            if (i & 1) lsum_b = f2_add(lsum_b, p2); else lsum_a = f2_add(lsum_a, p2);
+            float p0, p1;
+            f2_unpack(p2, p0, p1);
+            pk[i] = pack_bf16x2(p0, p1);
           }
-          l += lsum;
-        } else {
-          // exponentials two at a time: one FFMA2 scales and shifts a pair, the row sum is a pair of FADD2 chains,
-          // and the share of the exponentials that runs on the FMA pipes (poly_exp2_x2) is packed as well
-          const uint64_t scale2 = f2_bcast(p.scale_log2), nmref2 = f2_bcast(-mref);
-          uint64_t lsum_a = f2_bcast(0.f), lsum_b = f2_bcast(0.f);
-  #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t pk[16];
-  #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const uint64_t x2 = f2_fma(f2_pack(s[c * 32 + 2 * i], s[c * 32 + 2 * i + 1]), scale2, nmref2);
-              uint64_t p2;
-              if (exp2_pair_on_fma<kPolyOf8>(i)) {
-                p2 = poly_exp2_x2(x2);
-              } else {
-                float x0, x1;
-                f2_unpack(x2, x0, x1);
-                p2 = f2_pack(fast_exp2(x0), fast_exp2(x1));
-              }
-              if (i & 1) lsum_b = f2_add(lsum_b, p2); else lsum_a = f2_add(lsum_a, p2);
-              float p0, p1;
-              f2_unpack(p2, p0, p1);
-              pk[i] = pack_bf16x2(p0, p1);
-            }
-            tmem_st_x16(tS + c * 16, pk);
-          }
-          {
-            float la, lb;
-            f2_unpack(f2_add(lsum_a, lsum_b), la, lb);
-            l += la + lb;
-          }
+          tmem_st_x16(tS + c * 16, pk);
+        }
+        {
+          float la, lb;
+          f2_unpack(f2_add(lsum_a, lsum_b), la, lb);
+          l += la + lb;
         }
         tmem_st_wait();
         tc_fence_before();
@@ -442,6 +373,7 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tmem_dealloc(tmem, 512);
   }
 }
+
 
 }  // namespace dta
 
@@ -492,14 +424,8 @@ extern "C" int dta_tree_attn_fwd(const void* q, const void* k, const void* v, vo
     // share of the exponentials computed on the FMA pipes; DTA_FWD_POLY (0, 2, 4, 6 or 8 of every 8) is a tuning knob
     const char* e = getenv("DTA_FWD_POLY");
     const int poly = e ? atoi(e) : kDefaultFwdPoly;
-    const char* ve = getenv("DTA_FWD_VARIANT");
-    const int variant = ve ? atoi(ve) : kDefaultFwdVariant;
-#define DTA_FWD_PICK(V) (poly <= 1 ? tree_attn_fwd_kernel<0, V> : poly <= 3 ? tree_attn_fwd_kernel<2, V> : tree_attn_fwd_kernel<4, V>)
-    kernel = variant == 1 ? DTA_FWD_PICK(1) : variant == 2 ? DTA_FWD_PICK(2) : variant == 3 ? DTA_FWD_PICK(3)
-           : variant == 5 ? DTA_FWD_PICK(5) : variant == 7 ? DTA_FWD_PICK(7)
-           : (poly <= 0 ? tree_attn_fwd_kernel<0, 0> : poly == 1 ? tree_attn_fwd_kernel<1, 0> : poly == 2 ? tree_attn_fwd_kernel<2, 0>
-              : poly == 3 ? tree_attn_fwd_kernel<3, 0> : tree_attn_fwd_kernel<4, 0>);
-#undef DTA_FWD_PICK
+    kernel = poly <= 1 ? tree_attn_fwd_kernel<0> : poly <= 3 ? tree_attn_fwd_kernel<2>
+           : poly <= 5 ? tree_attn_fwd_kernel<4> : poly <= 7 ? tree_attn_fwd_kernel<6> : tree_attn_fwd_kernel<8>;
     DTA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
   const int grid = p.n_tiles * p.n_kv_heads * p.pairs_per_kv;
