@@ -5,12 +5,17 @@
 // (tree_training_engine.py:404-465), by ONE pass per layer over the linearised trie.
 //
 // Work decomposition
-//   CTA        = one 128-key tile x one KV head.  It loops over the query heads of the GQA
-//                group and over the key tile's LIVE query tiles, which form one contiguous
-//                range [tile, k_qlast[tile]] because every key's visible queries are the
-//                interval [k, subtree_end[k]).  dK/dV accumulate in TMEM across the whole
-//                loop (no atomics); dQ tiles are reduced into an fp32 accumulator with
-//                red.global.add.f32 (coalesced: lanes = head-dim index) and converted to bf16 by a second kernel.
+//   CTA        = one 128-key tile x one KV head x one chunk of the tile's LIVE query tiles.  The live
+//                query tiles of a key tile form one contiguous range [tile, k_qlast[tile]] because every
+//                key's visible queries are the interval [k, subtree_end[k]).  The CTA loops over the
+//                query heads of the GQA group and over its chunk; dK/dV accumulate in TMEM across the
+//                whole loop.  Normally the chunk is the whole range and dK/dV are written once, in bf16.
+//                A key tile of a shared trunk is visible to EVERY later query tile: when its range is
+//                longer than an even share of the launch (bwd_work_kernel), it is split over several
+//                CTAs, which add their fp32 partial dK/dV into an accumulator with 16-byte vector reds
+//                (converted by the epilogue kernel) -- otherwise one CTA would be the long pole of bushy
+//                tries.  dQ tiles leave through shared memory + TMA tensor reduce-add into an fp32
+//                accumulator and are converted to bf16 by the same epilogue kernel.
 //   per step   = 5 GEMMs, all 128x128x128 bf16 -> fp32 on tcgen05:
 //                  S^T  = K  Q^T     (SS, both K-major)            -> TMEM R0
 //                  dP^T = V  dO^T    (SS, both K-major)            -> TMEM R1
@@ -78,6 +83,10 @@ struct BwdParams {
   const int32_t* kmin_end;
   const int32_t* k_order;
   const int32_t* k_qlast;
+  const int4* work;        // [work_cap] {key tile, first query tile, query tiles, split?}  (bwd_work_kernel)
+  const int32_t* n_work;   // [1] number of valid work items
+  float* dk_acc;           // [n_pad, Hkv, 128] fp32: dK of key tiles whose query range is split over several CTAs
+  float* dv_acc;           // same for dV
   int n_nodes, n_pad, n_q_heads, n_kv_heads, group;
   int64_t k_row_stride, k_head_stride, v_row_stride, v_head_stride;
   float scale, scale_log2, inv_scale;
@@ -95,6 +104,9 @@ struct BwdParams {
 // trace mode 2 (debug flag 32): per compute warp, slot w = P^T pass done, slot 8 + w = dS^T pass done
 __device__ __forceinline__ void red_add_f32(float* addr, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {   // 16-byte aligned
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // kPolyOf8: how many of every 8 exponentials of the P^T pass run on the FMA pipes (poly_exp2)
@@ -132,10 +144,15 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int jt = p.k_order[blockIdx.x / p.n_kv_heads];   // key tile
+  const int widx = blockIdx.x / p.n_kv_heads;
+  if (widx >= *p.n_work) return;                          // the grid is sized for the worst-case number of chunks
+  const int4 item = p.work[widx];
+  const int jt = item.x;                                  // key tile
+  const int q_first = item.y;                             // first query tile of this CTA's chunk
+  const int n_qt = item.z;                                // query tiles in the chunk
+  const bool split = item.w != 0;                         // other CTAs hold the rest of this key tile's range
   const int kvh = blockIdx.x % p.n_kv_heads;
   const int k0 = jt * kT;
-  const int n_qt = p.k_qlast[jt] - jt + 1;
   const int n_iter = n_qt * p.group;
   const int kmin_end = p.kmin_end[jt];
 
@@ -199,7 +216,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // MMA of step it: one stage, reloaded as soon as dV(it) retires, has a whole step of slack.
       for (int it = 0; it < n_iter; ++it) {
         const int head = kvh * p.group + it / n_qt;
-        const int q0 = (jt + it % n_qt) * kT;
+        const int q0 = (q_first + it % n_qt) * kT;
         const int st = it % kQStages;
         const uint32_t ph = (it / kQStages) & 1;
         mbar_wait(bar_q_empty + st, ph ^ 1);
@@ -217,7 +234,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (p.l2_ahead > 0 && it + p.l2_ahead < n_iter) {
           const int it2 = it + p.l2_ahead;
           const int head2 = kvh * p.group + it2 / n_qt;
-          const int q2 = (jt + it2 % n_qt) * kT;
+          const int q2 = (q_first + it2 % n_qt) * kT;
           for (int h = 0; h < 2; ++h) {
             tma_prefetch_l2_3d(&tmap_q, h * 64, head2, q2);
             tma_prefetch_l2_3d(&tmap_do, h * 64, head2, q2);
@@ -367,7 +384,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const int k_end = k_idx < p.n_nodes ? p.subtree_end[k_idx] : 0;
 
     for (int it = 0; it < n_iter; ++it) {
-      const int qt = jt + it % n_qt;
+      const int qt = q_first + it % n_qt;
       const int qbase = qt * kT + ch * 64;
       const bool partial = !(qt > jt && kmin_end >= (qt + 1) * kT);
       const int vis_lo = k_idx - qbase, vis_hi = k_end - qbase;      // visible columns of this row: [lo, hi)
@@ -451,7 +468,28 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // ---- epilogue: dV, dK -> bf16 ----------------------------------------------------------
     mbar_wait(bar_dkv_full, 0);
     tc_fence_after();
-    if (true) {
+    if (split) {
+      // partial sums of a split key tile: fp32 vector reds (16 bytes per lane; a lane owns one key row)
+      float* dv_acc = p.dv_acc + (static_cast<int64_t>(k_idx) * p.n_kv_heads + kvh) * kT + ch * 64;
+      float* dk_acc = p.dk_acc + (static_cast<int64_t>(k_idx) * p.n_kv_heads + kvh) * kT + ch * 64;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        uint32_t a[32], b[32];
+        tmem_ld_x32(RdV + lane_addr + ch * 64 + part * 32, a);
+        tmem_ld_x32(RdK + lane_addr + ch * 64 + part * 32, b);
+        tmem_ld_wait();
+        if (k_idx < p.n_nodes) {
+          const float is = p.inv_scale;        // P^T was carried pre-multiplied by scale
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            red_add_v4_f32(dv_acc + part * 32 + i, __uint_as_float(a[i]) * is, __uint_as_float(a[i + 1]) * is,
+                           __uint_as_float(a[i + 2]) * is, __uint_as_float(a[i + 3]) * is);
+            red_add_v4_f32(dk_acc + part * 32 + i, __uint_as_float(b[i]), __uint_as_float(b[i + 1]),
+                           __uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
+          }
+        }
+      }
+    } else {
       __nv_bfloat16* dv_row = p.dv + static_cast<int64_t>(k_idx) * p.v_row_stride + static_cast<int64_t>(kvh) * p.v_head_stride + ch * 64;
       __nv_bfloat16* dk_row = p.dk + static_cast<int64_t>(k_idx) * p.k_row_stride + static_cast<int64_t>(kvh) * p.k_head_stride + ch * 64;
 #pragma unroll
@@ -489,7 +527,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) << 5) << 16;
     for (int it = 0; it < n_iter; ++it) {
       const int head = kvh * p.group + it / n_qt;
-      const int q0 = (jt + it % n_qt) * kT;
+      const int q0 = (q_first + it % n_qt) * kT;
       mbar_wait(bar_dq_full, it & 1);
       if (threadIdx.x == 256) DTA_TRACE(10);
       tc_fence_after();
@@ -568,6 +606,116 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------
+// Work list of the main kernel (one CTA, once per call; n_tiles <= a few thousand).  Key tile t has
+// n_qt(t) = k_qlast[t] - t + 1 live query tiles and is one job per KV head.  With share = the (tile, head) steps an
+// SM gets when the launch is perfectly balanced, a tile longer than HALF a share,
+//   L = max(kMinSplitTiles, ceil(share / 2)),   share = ceil(n_kv_heads * sum_t n_qt(t) / n_sm),
+// is cut into ceil(n_qt / L) chunks of equal size (ordering: see below); shorter tiles cannot unbalance an LPT
+// schedule by more than that and stay whole -- splitting is not free (chunks re-read K/V, leave through fp32 reds,
+// and thin out the lock-step that keeps Q / dO in L2: 1-3 % on tries that do not need it).
+// sum(chunks) <= n_tiles + 2 n_sm / n_kv_heads, which sizes the grid on the host without a device read-back.
+// ------------------------------------------------------------------------------------
+static constexpr int kMinSplitTiles = 16;
+
+__global__ void __launch_bounds__(1024) bwd_work_kernel(const int32_t* __restrict__ k_order,
+                                                        const int32_t* __restrict__ k_qlast, int n_tiles, int n_sm,
+                                                        int n_kv_heads, int enable_split, int4* __restrict__ work, int32_t* __restrict__ n_work,
+                                                        int32_t* __restrict__ k_split) {
+  __shared__ int s_warp[32];
+  __shared__ int s_bcast;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto block_scan = [&](int v, int& total) {          // exclusive scan over the 1024 threads
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane], winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      s_warp[lane] = winc - w;
+      if (lane == 31) s_bcast = winc;
+    }
+    __syncthreads();
+    const int excl = s_warp[warp] + inc - v;
+    total = s_bcast;
+    __syncthreads();
+    return excl;
+  };
+  __shared__ int s_max;
+  if (tid == 0) s_max = 0;
+  __syncthreads();
+  int local = 0, local_max = 0;
+  for (int i = tid; i < n_tiles; i += blockDim.x) {
+    const int n = k_qlast[i] - i + 1;
+    local += n;
+    local_max = max(local_max, n);
+  }
+  atomicMax(&s_max, local_max);
+  int total;
+  (void)block_scan(local, total);                      // (its barriers also publish s_max)
+  const int share = static_cast<int>((static_cast<int64_t>(total) * n_kv_heads + n_sm - 1) / n_sm);
+  const int split_len = enable_split ? max(kMinSplitTiles, (share + 1) / 2) : (1 << 30);
+  const int max_parts = (s_max + split_len - 1) / split_len;
+  // Order: chunk 0 of every split tile (k_order sequence), then chunk 1 of every split tile, ..., then the unsplit
+  // tiles.  Heavy items first (LPT), and the CTAs resident at the same time walk the SAME query range, which is
+  // what keeps their Q / dO loads and dQ reductions meeting in L2 (interleaving a tile's chunks costs 7 %).
+  int base = 0;
+  for (int c = 0; c <= max_parts; ++c) {               // c == max_parts: the unsplit tiles
+    if (c < max_parts && max_parts == 1) continue;     // nothing is split
+    for (int start = 0; start < n_tiles; start += blockDim.x) {
+      const int pos = start + tid;
+      int jt = 0, n_qt = 0, parts = 0;
+      if (pos < n_tiles) {
+        jt = k_order[pos];
+        n_qt = k_qlast[jt] - jt + 1;
+        parts = (n_qt + split_len - 1) / split_len;
+      }
+      const bool emit = pos < n_tiles && (c == max_parts ? parts == 1 : (parts > 1 && c < parts));
+      int chunk_total;
+      const int off = block_scan(emit ? 1 : 0, chunk_total);
+      if (emit) {
+        if (c == max_parts) {
+          k_split[jt] = 0;
+          work[base + off] = make_int4(jt, jt, n_qt, 0);
+        } else {
+          k_split[jt] = 1;
+          const int lo = static_cast<int>(static_cast<int64_t>(c) * n_qt / parts);
+          const int hi = static_cast<int>(static_cast<int64_t>(c + 1) * n_qt / parts);
+          work[base + off] = make_int4(jt, jt + lo, hi - lo, 1);
+        }
+      }
+      base += chunk_total;
+    }
+  }
+  if (tid == 0) *n_work = base;
+}
+
+// rows of split key tiles in the fp32 dK / dV accumulators ([n_pad, Hkv, 128] each, dv right behind dk)
+__device__ __forceinline__ void zero_split_rows(const int32_t* __restrict__ k_split, int n_tiles, int n_kv_heads,
+                                                float* __restrict__ dk_acc, float* __restrict__ dv_acc) {
+  const int64_t per_tile = static_cast<int64_t>(kT) * n_kv_heads * (kT / 4);       // float4 per tile and buffer
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t n_thr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int t = 0; t < n_tiles; ++t) {
+    if (!k_split[t]) continue;
+    float4* a = reinterpret_cast<float4*>(dk_acc) + t * per_tile;
+    float4* b = reinterpret_cast<float4*>(dv_acc) + t * per_tile;
+    for (int64_t i = tid; i < per_tile; i += n_thr) {
+      a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Pre-pass (one warp per (q, h) row; HBM-bound): delta[h, q] = sum_d dO[q,h,d] * O[q,h,d] and the exponent
 // offset L = (log2(scale) - lse2[h, q]) / scale_log2, each written as a 3-term bf16 split into a 16-byte
 // row {hi, mid, lo, 0, 0, 0, 0, 0} -- the B operand rows of the main kernel's broadcast k-step, which
@@ -589,7 +737,10 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
                                                          int n_pad, int n_heads, int64_t row_stride,
                                                          int64_t head_stride, const float* __restrict__ lse2,
                                                          float lshift, float inv_scale_log2,
-                                                         uint4* __restrict__ aug_lse, uint4* __restrict__ aug_delta) {
+                                                         uint4* __restrict__ aug_lse, uint4* __restrict__ aug_delta,
+                                                         const int32_t* __restrict__ k_split, int n_kv_heads,
+                                                         float* __restrict__ dk_acc, float* __restrict__ dv_acc) {
+  zero_split_rows(k_split, n_pad / kT, n_kv_heads, dk_acc, dv_acc);
   // half-warp per (q, h) row, 16 bytes per lane and tensor, four row pairs loaded before the first is reduced
   const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   const int64_t n_rows = static_cast<int64_t>(n_pad) * n_heads;
@@ -635,9 +786,45 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 }
 
 // dq (bf16, q strides) <- dq_accum (fp32 [n_pad, Hq, 128])
+// + for key tiles whose query range was split: dk / dv (bf16, k / v strides) <- the fp32 partial-sum accumulators
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, int n_nodes, int n_heads,
                                                               int64_t row_stride, int64_t head_stride,
-                                                              __nv_bfloat16* __restrict__ dq) {
+                                                              __nv_bfloat16* __restrict__ dq,
+                                                              const int32_t* __restrict__ k_split, int n_tiles,
+                                                              int n_kv_heads, const float* __restrict__ dk_acc,
+                                                              const float* __restrict__ dv_acc, int64_t k_row_stride,
+                                                              int64_t k_head_stride, int64_t v_row_stride,
+                                                              int64_t v_head_stride, __nv_bfloat16* __restrict__ dk,
+                                                              __nv_bfloat16* __restrict__ dv) {
+  {
+    const int64_t per_tile = static_cast<int64_t>(kT) * n_kv_heads * (kT / 8);     // 8-element vectors per tile
+    const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t n_thr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int t = 0; t < n_tiles; ++t) {
+      if (!k_split[t]) continue;
+      for (int64_t i = tid; i < per_tile; i += n_thr) {
+        const int c = static_cast<int>(i % (kT / 8)) * 8;
+        const int64_t rh = i / (kT / 8);
+        const int h = static_cast<int>(rh % n_kv_heads);
+        const int64_t k = static_cast<int64_t>(t) * kT + rh / n_kv_heads;
+        if (k >= n_nodes) continue;
+        const int64_t src = (k * n_kv_heads + h) * kT + c;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          const float* a_ = (which ? dv_acc : dk_acc) + src;
+          const float4 a = __ldcs(reinterpret_cast<const float4*>(a_));
+          const float4 b = __ldcs(reinterpret_cast<const float4*>(a_ + 4));
+          uint4 w;
+          w.x = pack_bf16x2(a.x, a.y);
+          w.y = pack_bf16x2(a.z, a.w);
+          w.z = pack_bf16x2(b.x, b.y);
+          w.w = pack_bf16x2(b.z, b.w);
+          __nv_bfloat16* dst = which ? dv + k * v_row_stride + h * v_head_stride + c : dk + k * k_row_stride + h * k_head_stride + c;
+          *reinterpret_cast<uint4*>(dst) = w;
+        }
+      }
+    }
+  }
   const int64_t n_vec = static_cast<int64_t>(n_nodes) * n_heads * (kT / 8);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_vec;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -662,6 +849,31 @@ using namespace dta;
 
 static long long* g_bwd_trace = nullptr;
 
+// Workspace: [dq_accum fp32 | lse operand rows | delta operand rows | work items | n_work | k_split | dk_acc | dv_acc]
+struct BwdWorkspace {
+  size_t dq, aug_lse, aug_delta, work, n_work, k_split, dk_acc, dv_acc, total;
+  int work_cap;
+};
+static BwdWorkspace bwd_workspace_layout(const dta_attn_shape_t* sh, int n_sm) {
+  auto up = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+  BwdWorkspace w;
+  const int n_tiles = sh->n_pad / DTA_TILE;
+  w.work_cap = n_tiles + (2 * n_sm + sh->n_kv_heads - 1) / sh->n_kv_heads + 1;   // see bwd_work_kernel
+  const size_t aug = static_cast<size_t>(sh->n_pad) * sh->n_q_heads * 16;     // one 16-byte operand row per (head, query)
+  const size_t dkv = static_cast<size_t>(sh->n_pad) * sh->n_kv_heads * kT * sizeof(float);
+  size_t o = 0;
+  w.dq = o;        o = up(o + static_cast<size_t>(sh->n_pad) * sh->n_q_heads * kT * sizeof(float));
+  w.aug_lse = o;   o = up(o + aug);
+  w.aug_delta = o; o = up(o + aug);
+  w.work = o;      o = up(o + static_cast<size_t>(w.work_cap) * sizeof(int4));
+  w.n_work = o;    o = up(o + 16);
+  w.k_split = o;   o = up(o + static_cast<size_t>(n_tiles) * sizeof(int32_t));
+  w.dk_acc = o;    o = up(o + dkv);
+  w.dv_acc = o;    o = up(o + dkv);
+  w.total = o;
+  return w;
+}
+
 extern "C" {
 
 /* debug only (not in the public header): device buffer of 48*16 int64 receiving the step timeline of CTA 0 */
@@ -669,9 +881,7 @@ int dta_debug_set_bwd_trace(long long* buf) { g_bwd_trace = buf; return 0; }
 
 size_t dta_tree_attn_bwd_workspace_bytes(const dta_attn_shape_t* sh) {
   if (!sh) return 0;
-  const size_t dq = static_cast<size_t>(sh->n_pad) * sh->n_q_heads * kT * sizeof(float);
-  const size_t aug = static_cast<size_t>(sh->n_pad) * sh->n_q_heads * 16;     // one 16-byte operand row per (head, query)
-  return dq + 2 * aug + 256;
+  return bwd_workspace_layout(sh, sm_count()).total;
 }
 
 int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
@@ -695,11 +905,23 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
                   sh->o_row_stride % 8 == 0 && sh->o_head_stride % 8 == 0,
               "strides must be multiples of 8 elements");
 
-  float* dq_accum = static_cast<float*>(workspace);
+  const BwdWorkspace wl = bwd_workspace_layout(sh, sm_count());
+  uint8_t* ws8 = static_cast<uint8_t*>(workspace);
+  float* dq_accum = reinterpret_cast<float*>(ws8 + wl.dq);
   const size_t dq_bytes = static_cast<size_t>(sh->n_pad) * sh->n_q_heads * kT * sizeof(float);
-  uint4* aug_lse = reinterpret_cast<uint4*>(static_cast<uint8_t*>(workspace) + dq_bytes);
-  uint4* aug_delta = aug_lse + static_cast<size_t>(sh->n_pad) * sh->n_q_heads;
+  uint4* aug_lse = reinterpret_cast<uint4*>(ws8 + wl.aug_lse);
+  uint4* aug_delta = reinterpret_cast<uint4*>(ws8 + wl.aug_delta);
+  int4* work = reinterpret_cast<int4*>(ws8 + wl.work);
+  int32_t* n_work = reinterpret_cast<int32_t*>(ws8 + wl.n_work);
+  int32_t* k_split = reinterpret_cast<int32_t*>(ws8 + wl.k_split);
+  float* dk_acc = reinterpret_cast<float*>(ws8 + wl.dk_acc);
+  float* dv_acc = reinterpret_cast<float*>(ws8 + wl.dv_acc);
+  const int n_tiles_ = sh->n_pad / DTA_TILE;
   DTA_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, dq_bytes, stream));
+  const int enable_split = getenv("DTA_BWD_SPLIT") ? atoi(getenv("DTA_BWD_SPLIT")) : 1;   // 0: one CTA per key tile (A/B knob)
+  bwd_work_kernel<<<1, 1024, 0, stream>>>(meta->k_order, meta->k_qlast, n_tiles_, sm_count(), sh->n_kv_heads, enable_split, work, n_work,
+                                          k_split);
+  DTA_CHECK_CUDA(cudaGetLastError());
 
   const int64_t n_rows = static_cast<int64_t>(sh->n_pad) * sh->n_q_heads;
   {
@@ -709,7 +931,7 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
     attn_delta_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), sh->n_nodes, sh->n_pad,
         sh->n_q_heads, sh->o_row_stride, sh->o_head_stride, lse, log2f(sh->scale), 1.0f / (sh->scale * kLog2e),
-        aug_lse, aug_delta);
+        aug_lse, aug_delta, k_split, sh->n_kv_heads, dk_acc, dv_acc);
     DTA_CHECK_CUDA(cudaGetLastError());
   }
 
@@ -732,6 +954,10 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   p.kmin_end = meta->kmin_end;
   p.k_order = meta->k_order;
   p.k_qlast = meta->k_qlast;
+  p.work = work;
+  p.n_work = n_work;
+  p.dk_acc = dk_acc;
+  p.dv_acc = dv_acc;
   p.n_nodes = sh->n_nodes;
   p.n_pad = sh->n_pad;
   p.n_q_heads = sh->n_q_heads;
@@ -766,7 +992,8 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   const int n_tiles = sh->n_pad / DTA_TILE;
   const ProfileHook hook = take_profile_hook();
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
-  kernel<<<n_tiles * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, tdq, p);
+  (void)n_tiles;
+  kernel<<<wl.work_cap * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, tdq, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
 
@@ -775,9 +1002,10 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
     int64_t grid = (n_vec + 255) / 256;
     const int64_t cap = 16 * static_cast<int64_t>(sm_count());
     if (grid > cap) grid = cap;
-    attn_dq_convert_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(dq_accum, sh->n_nodes, sh->n_q_heads,
-                                                                       sh->q_row_stride, sh->q_head_stride,
-                                                                       static_cast<__nv_bfloat16*>(dq));
+    attn_dq_convert_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
+        dq_accum, sh->n_nodes, sh->n_q_heads, sh->q_row_stride, sh->q_head_stride, static_cast<__nv_bfloat16*>(dq),
+        k_split, n_tiles_, sh->n_kv_heads, dk_acc, dv_acc, sh->k_row_stride, sh->k_head_stride, sh->v_row_stride,
+        sh->v_head_stride, static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv));
     DTA_CHECK_CUDA(cudaGetLastError());
   }
   return DTA_OK;

@@ -117,7 +117,10 @@ int dta_tree_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
  * (cudaEvent_t handles, on the call's stream), then the hook clears itself.  NULLs disarm it. */
 int dta_profile_next_attn(void* start_event, void* stop_event);
 
-/* Workspace: fp32 dq accumulator [N,Hq,D] + delta [Hq,n_pad] + shifted lse [Hq,n_pad]. */
+/* Workspace (256-byte aligned, contents need not be initialised): fp32 dq accumulator [n_pad,Hq,D], the lse / delta
+ * operand rows [Hq,n_pad] x 16 B each, the launch's work list (key tile x chunk of its live query tiles; a trunk tile
+ * that would be the launch's long pole is split over several CTAs), and fp32 dk / dv accumulators [n_pad,Hkv,D] for
+ * the split tiles.  About (4*Hq + 8*Hkv) * D + 32*Hq bytes per node. */
 size_t dta_tree_attn_bwd_workspace_bytes(const dta_attn_shape_t* shape);
 
 /* dout uses the o strides; dq uses the q strides, dk the k strides, dv the v strides. */

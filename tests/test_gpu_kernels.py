@@ -223,6 +223,31 @@ def test_tree_attention_strided_views_and_lse():
     assert _rel(out, ref) < 5e-3
 
 
+def test_chain_equals_dense_causal_sdpa():
+    """A trie with one leaf is dense causal attention: the kernels against torch's own SDPA (fp32, is_causal,
+    GQA by head repetition) on a ragged 16k-class length -- the dense-causal equivalent the reference compares its
+    tree path with (dense.py)."""
+    import torch.nn.functional as F
+    from dynamictreeattn_b200.attention import tree_attention
+    from dynamictreeattn_b200.linearize import linearize_trie
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    g = torch.Generator().manual_seed(3)
+    N, Hq, Hkv = 4096 + 77, 4, 2
+    lay = linearize_trie(TokenTrie([torch.randint(0, 1000, (N,), generator=g)]), "cuda")
+    q, k, v, do = _qkv(N, Hq, Hkv)
+    q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+    out = tree_attention(q, k, v, lay, 128 ** -0.5)
+    out.backward(do)
+    qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    rep = Hq // Hkv
+    ref = F.scaled_dot_product_attention(qr.transpose(0, 1)[None], kr.transpose(0, 1).repeat_interleave(rep, 0)[None],
+                                         vr.transpose(0, 1).repeat_interleave(rep, 0)[None], is_causal=True,
+                                         scale=128 ** -0.5)[0].transpose(0, 1)
+    ref.backward(do.float())
+    assert _rel(out, ref) < 5e-3
+    assert _rel(q.grad, qr.grad) < 1e-2 and _rel(k.grad, kr.grad) < 1e-2 and _rel(v.grad, vr.grad) < 1e-2
+
+
 def test_constant_values_property_full_size():
     """Size-independent property at BASELINE size (tau2-16k shape, 67k trie tokens, Hq 16 / Hkv 8):
     with V == 1 every softmax row must sum to 1 -> out == 1 exactly up to bf16; and dV == sum over
