@@ -76,7 +76,7 @@ SIGNATURES = {
 # kernels launched per successful call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
     "dta_lcp_adjacent": 1, "dta_trie_linearize": 2, "dta_trie_paths": 1, "dta_tile_meta": 2,
-    "dta_tree_attn_fwd": 1, "dta_tree_attn_bwd": 3,
+    "dta_tree_attn_fwd": 1, "dta_tree_attn_bwd": 4,
     "dta_logprob_row_stats": 1, "dta_logprob_gather_labels": 1, "dta_logprob_finalize": 1,
     "dta_logprob_bwd": 1, "dta_logprob_bwd_scatter": 1, "dta_logprob_rowsum_grad": 1,
     "dta_rmsnorm_fwd": 1, "dta_rmsnorm_bwd": 1, "dta_qknorm_rope_fwd": 1, "dta_qknorm_rope_bwd": 1,
