@@ -876,6 +876,18 @@ static BwdWorkspace bwd_workspace_layout(const dta_attn_shape_t* sh, int n_sm) {
 
 extern "C" {
 
+/* debug / test only (not in the public header): the work list dta_tree_attn_bwd builds for a launch.
+ * work: int32[4 * cap] {key tile, first query tile, query tiles, split}, n_work: int32[1], k_split: int32[n_tiles];
+ * returns the capacity the caller must provide (cap) when work == NULL. */
+int dta_debug_bwd_work_list(const int32_t* k_order, const int32_t* k_qlast, int n_tiles, int n_sm, int n_kv_heads,
+                            int32_t* work, int32_t* n_work, int32_t* k_split, dta_stream_t stream) {
+  const int cap = n_tiles + (2 * n_sm + n_kv_heads - 1) / n_kv_heads + 1;
+  if (work == nullptr) return cap;
+  bwd_work_kernel<<<1, 1024, 0, stream>>>(k_order, k_qlast, n_tiles, n_sm, n_kv_heads, 1, reinterpret_cast<int4*>(work),
+                                          n_work, k_split);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 /* debug only (not in the public header): device buffer of 48*16 int64 receiving the step timeline of CTA 0 */
 int dta_debug_set_bwd_trace(long long* buf) { g_bwd_trace = buf; return 0; }
 

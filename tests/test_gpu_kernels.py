@@ -248,6 +248,60 @@ def test_chain_equals_dense_causal_sdpa():
     assert _rel(q.grad, qr.grad) < 1e-2 and _rel(k.grad, kr.grad) < 1e-2 and _rel(v.grad, vr.grad) < 1e-2
 
 
+@pytest.mark.parametrize("name", ["many_leaves", "deep_forks", "tau2_mini", "chain_300", "forest"])
+@pytest.mark.parametrize("n_sm,n_kv", [(148, 8), (148, 1), (8, 2)])
+def test_bwd_work_list_partitions_every_query_range(name, n_sm, n_kv):
+    """The backward launch's work list (split query ranges for long-pole key tiles): the chunks of every key tile
+    tile its live range [t, k_qlast[t]] exactly once, only tiles longer than half a balanced share are split, the
+    item count respects the bound that sizes the grid, and all chunks c of split tiles precede chunks c+1."""
+    from dynamictreeattn_b200 import _cabi
+    _cabi.load()
+    raw = C.CDLL(str(_cabi.lib_path()))
+    trie, lay = _layout(name)
+    n_tiles = lay.n_pad // 128
+    P = lambda t: C.c_void_p(t.data_ptr())
+    cap = raw.dta_debug_bwd_work_list(None, None, n_tiles, n_sm, n_kv, None, None, None, None)
+    work = torch.full((cap, 4), -1, dtype=torch.int32, device="cuda")
+    n_work = torch.zeros(1, dtype=torch.int32, device="cuda")
+    k_split = torch.full((n_tiles,), -1, dtype=torch.int32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert raw.dta_debug_bwd_work_list(P(lay.k_order), P(lay.k_qlast), n_tiles, n_sm, n_kv, P(work), P(n_work),
+                                       P(k_split), st) == 0
+    torch.cuda.synchronize()
+    n = int(n_work.item())
+    assert n_tiles <= n <= cap
+    items = work[:n].cpu().tolist()
+    k_qlast = lay.k_qlast.cpu().tolist()
+    n_qt = [k_qlast[t] - t + 1 for t in range(n_tiles)]
+    share = -(-sum(n_qt) * n_kv // n_sm)
+    limit = max(16, (share + 1) // 2)
+    cover = {t: [] for t in range(n_tiles)}
+    for jt, q_first, cnt, split in items:
+        assert 0 <= jt < n_tiles and cnt >= 1
+        cover[jt].append((q_first, cnt, split))
+    for t in range(n_tiles):
+        chunks = sorted(cover[t])
+        assert chunks[0][0] == t and sum(c for _, c, _ in chunks) == n_qt[t]
+        for (a, ca, _), (b, _, _) in zip(chunks, chunks[1:]):
+            assert a + ca == b                                            # contiguous, no overlap
+        parts = -(-n_qt[t] // limit)
+        assert len(chunks) == parts and all(s == (1 if parts > 1 else 0) for _, _, s in chunks)
+        assert int(k_split[t]) == (1 if parts > 1 else 0)
+        assert max(c for _, c, _ in chunks) - min(c for _, c, _ in chunks) <= 1
+    # order: split chunks first, grouped by chunk index; unsplit tiles last, in k_order sequence
+    seen_unsplit = False
+    last_chunk_idx = 0
+    for jt, q_first, cnt, split in items:
+        if not split:
+            seen_unsplit = True
+            continue
+        assert not seen_unsplit
+        idx = sorted(cover[jt]).index((q_first, cnt, split))
+        assert idx >= last_chunk_idx
+        last_chunk_idx = idx
+    assert [jt for jt, _, _, s in items if not s] == [t for t in lay.k_order.cpu().tolist() if len(cover[t]) == 1]
+
+
 def test_constant_values_property_full_size():
     """Size-independent property at BASELINE size (tau2-16k shape, 67k trie tokens, Hq 16 / Hkv 8):
     with V == 1 every softmax row must sum to 1 -> out == 1 exactly up to bf16; and dV == sum over
