@@ -106,13 +106,18 @@ pair_kernel(int mode, int n_dim, int iters, int interfere, float* out, long long
     const uint32_t idesc = mode == 2 ? make_idesc_bf16(128, n_dim, false, false) : make_idesc_bf16(256, n_dim, false, false);
     const long long t0 = clock64();
     if (issuer) {
-      for (int it = 0; it < iters; ++it) {
+      // 8 accumulation chains (4 k-steps each) per elected block: the issuing lane must not be the bottleneck
+      for (int it = 0; it < iters; it += (mode == 0 ? 1 : 8)) {
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kK / 16; ++kk) {
-            const uint32_t d = tmem + (mode == 0 ? 0 : (it & 1) * (n_dim > 128 ? 256 : 128));
-            if (mode == 2) umma_ss_lo(d, kA + kk * 2, kB + kk * 2, idesc, kk > 0);
-            else umma_ss_2cta(d, kA + kk * 2, kB + kk * 2, idesc, kk > 0);
+          for (int u = 0; u < 8; ++u) {
+            if (mode == 0 && u > 0) break;
+            const uint32_t d = tmem + (mode == 0 ? 0 : (u & 1) * (n_dim > 128 ? 256 : 128));
+#pragma unroll
+            for (int kk = 0; kk < kK / 16; ++kk) {
+              if (mode == 2) umma_ss_lo(d, kA + kk * 2, kB + kk * 2, idesc, kk > 0);
+              else umma_ss_2cta(d, kA + kk * 2, kB + kk * 2, idesc, kk > 0);
+            }
           }
         }
         __syncwarp();
@@ -192,7 +197,7 @@ int main() {
            err == 0 ? "PASS" : "FAIL");
   }
   // ---- rate
-  const int iters = 2000;
+  const int iters = 2048;
   struct Case { int mode, n, interfere; const char* name; };
   const Case cases[] = {{2, 128, 0, "cta_group::1 M=128 N=128"},          {2, 128, 1, "cta_group::1 M=128 N=128 + STS.128 x8 warps"},
                         {1, 128, 0, "cta_group::2 M=256 N=128"},          {1, 128, 1, "cta_group::2 M=256 N=128 + STS.128 x8 warps"},
