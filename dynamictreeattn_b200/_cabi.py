@@ -14,7 +14,8 @@ from typing import Optional
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libdta_b200.so"
+# DTA_LIB_PATH: load another build of the same ABI (A/B timing of kernel changes on one box); default: the in-tree build
+_LIB_PATH = Path(os.environ.get("DTA_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libdta_b200.so")
 _lib = None
 
 ABI_VERSION = 1

@@ -17,6 +17,12 @@ which is why the reference keeps whole logits rows at fork positions,
 tree_training_engine.py:217-220, 369-372).  The result is mathematically the reference's
  and independent of ``block_size`` / ``cut_f1_tail`` / leaf order,
 which are accepted for compatibility: ``block_size`` only sizes the head's row chunks.
+
+Memory.  The reference's footprint is bounded by the stack depth; one linearised pass keeps the activations of
+all N trie tokens (~1.4 MB per token for Qwen3-0.6B).  A trie over the engine's token budget
+(``max_trie_tokens``; by default derived from free HBM) is therefore cut into contiguous DFS ranges of sequences
+with the reference's own partitioner (``LB_by_DFS_and_TM``) and the ranges run one after the other: losses add,
+gradients accumulate, the shared prefix of a cut is recomputed once per range — same result, bounded memory.
 """
 from __future__ import annotations
 
@@ -196,7 +202,67 @@ class TreeTrainingEngine:
         self.head_chunk_rows = 8192
         self.keep_head_logits = True     # keep bf16 logits between the head's two passes when HBM allows
         self.use_fused_trunk = True      # Qwen3-style bf16 models; others go through the HF attention plugin
+        self.max_trie_tokens: Optional[int] = None    # None: derive from free HBM (CUDA) / unlimited (elsewhere)
         self.last_layout: Optional[TrieLayout] = None
+        self.last_n_ranges = 1           # sub-tries the last forward/backward call ran as
+        self._budget_cache = {}
+
+    # ---- memory-bounded execution ------------------------------------------------------------
+    def _token_budget(self, training: bool) -> Optional[int]:
+        """Trie tokens one linearised pass may hold.  Saved activations per token and layer (bf16): 7 hidden-wide
+        rows, q/k/v and their normed copies, the attention output, three MLP-wide rows; the backward adds fp32
+        dq/dk/dv accumulators and gradients of the same shapes."""
+        if self.max_trie_tokens is not None:
+            return int(self.max_trie_tokens)
+        if self.device.type != "cuda":
+            return None
+        key = (id(self.model), training)
+        if key in self._budget_cache:                    # cudaMemGetInfo once per model, not once per step
+            return self._budget_cache[key]
+        cfg = self.model_config
+        hq = cfg.num_attention_heads
+        inter = getattr(cfg, "intermediate_size", 4 * cfg.hidden_size)
+        per_layer = 7 * cfg.hidden_size + (3 * hq + 3 * self.n_kv_heads) * self.head_dim + 3 * inter
+        per_token = 2 * per_layer * (self.n_layers if training else 2) + 16 * (hq + self.n_kv_heads) * self.head_dim
+        free, _ = torch.cuda.mem_get_info(self.device)
+        free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        usable = free - (16 << 30)                       # head chunks, workspaces, allocator slack
+        self._budget_cache[key] = max(int(0.85 * usable / per_token), 4096)
+        return self._budget_cache[key]
+
+    @staticmethod
+    def _sequences_of(token_trie):
+        """(tokens, attach) of every original sequence of a trie (leaf i holds its folded prefixes)."""
+        out = []
+        for ids, attach_list in zip(token_trie.inputs, token_trie.attach_lists):
+            for attach, length in attach_list:
+                out.append((ids[:length], attach))
+        return out
+
+    def _ranges(self, token_trie, budget: int):
+        """Cut a trie that exceeds ``budget`` trie tokens into sub-tries of contiguous DFS ranges; None if it fits
+        (or cannot be cut).  Attach dicts are shallow copies that keep the ORIGINAL ``_sequence_batch_id``."""
+        from .data_parallel import partition
+        from .token_trie import TokenTrie
+        n_tok = sum(token_trie.lens) - sum(token_trie.lcp_lens)      # trie tokens (trie.py:8-13)
+        if n_tok <= budget or token_trie.n_sequences < 2:
+            return None
+        seqs = self._sequences_of(token_trie)
+        toks = [t for t, _ in seqs]
+        k = min(len(seqs), -(-n_tok // budget))
+        while True:
+            bins = [b for b in partition(toks, k, "LB_by_DFS_and_TM", None, "backward", None) if b]
+            tries = []
+            for b in bins:
+                att = [dict(seqs[i][1]) for i in b]
+                t = TokenTrie([toks[i] for i in b], att)
+                for a, i in zip(att, b):
+                    a["_sequence_batch_id"] = seqs[i][1].get("_sequence_batch_id", i)
+                tries.append(t)
+            worst = max(t.get_stats("forward")["n_tree_tokens"] for t in tries)
+            if worst <= budget or k >= len(seqs):
+                return tries
+            k = min(len(seqs), max(k + 1, -(-k * worst // budget)))
 
     # ---- shared pieces ---------------------------------------------------------------------
     def _check_lengths(self, token_trie) -> None:
@@ -265,6 +331,22 @@ class TreeTrainingEngine:
         returns: List[Optional[torch.Tensor]] = [None] * token_trie.n_sequences
         if not token_trie.inputs:
             return returns
+        budget = self._token_budget(training=False)
+        ranges = self._ranges(token_trie, budget) if budget is not None else None
+        self.last_n_ranges = len(ranges) if ranges else 1
+        if ranges:
+            for sub in ranges:
+                sub.forward_permute()
+                for sid, lp in self._forward_one(model, sub).items():
+                    returns[sid] = lp
+            return returns
+        for sid, lp in self._forward_one(model, token_trie).items():
+            returns[sid] = lp
+        return returns
+
+    def _forward_one(self, model, token_trie) -> dict:
+        """{_sequence_batch_id: log-probs} of one trie that fits the budget."""
+        returns = {}
         layout = linearize_trie(token_trie, self.device)
         self.last_layout = layout
         h = self._trunk(model, layout)
@@ -284,6 +366,15 @@ class TreeTrainingEngine:
         self._check_lengths(token_trie)
         if not token_trie.inputs:
             return 0.0
+        budget = self._token_budget(training=True)
+        ranges = self._ranges(token_trie, budget) if budget is not None else None
+        self.last_n_ranges = len(ranges) if ranges else 1
+        if ranges:
+            total = 0.0
+            for sub in ranges:
+                sub.backward_permute()
+                total += self.backward_layout(model, sub, linearize_trie(sub, self.device), loss_fn, block_size)
+            return total
         layout = linearize_trie(token_trie, self.device)
         return self.backward_layout(model, token_trie, layout, loss_fn, block_size)
 

@@ -141,3 +141,43 @@ def test_custom_loss_fn_with_token_coupling(cpu_backend):
     trie.backward_permute()
     lt = TreeTrainingEngine(cfg, "cpu", torch.float32, 4096).backward(model, trie, loss_fn, block_size=32)
     assert abs(lt - ld) < 1e-4 and worst_ratio(grads(model), gd) < 1e-5
+
+
+def test_memory_bounded_ranges_give_the_same_result(cpu_backend):
+    """A trie over the engine's token budget runs as several sub-tries (contiguous DFS ranges from the reference's
+    partitioner): same loss, same gradients, same per-sequence log-probs, original sequence ids preserved."""
+    cfg, model = tiny_model()
+    seqs = config1_seqs()                              # 9 sequences (one pure prefix), 352 trie tokens
+    seen = []
+
+    def loss_fn(lp, ent, a):
+        seen.append(a["_sequence_batch_id"])
+        return tree_oracle.example_loss(lp, ent, a) * (1 + 0.1 * a["_sequence_batch_id"])
+
+    eng = TreeTrainingEngine(cfg, "cpu", torch.float32, 4096)
+    trie = TokenTrie(seqs, attachs(len(seqs)))
+    trie.backward_permute()
+    loss_whole = eng.backward(model, trie, loss_fn, block_size=None)
+    assert eng.last_n_ranges == 1 and sorted(seen) == list(range(9))
+    g_whole = grads(model)
+    model.zero_grad(set_to_none=True)
+    lp_whole = eng.forward(model, TokenTrie(seqs))
+
+    seen.clear()
+    eng.max_trie_tokens = 150                          # forces >= 3 ranges; shared trunk recomputed per range
+    trie = TokenTrie(seqs, attachs(len(seqs)))
+    trie.backward_permute()
+    loss_split = eng.backward(model, trie, loss_fn, block_size=None)
+    assert eng.last_n_ranges >= 3 and sorted(seen) == list(range(9))
+    assert abs(loss_split - loss_whole) < 1e-4 * max(1.0, abs(loss_whole))
+    assert worst_ratio(grads(model), g_whole) < 1e-5
+    lp_split = eng.forward(model, TokenTrie(seqs))
+    assert eng.last_n_ranges >= 3 and len(lp_split) == 9
+    for a, b in zip(lp_whole, lp_split):
+        assert a.shape == b.shape and torch.allclose(a, b, atol=1e-5)
+    # a budget below the longest sequence cannot be met: one sequence per range is the floor, not an error
+    eng.max_trie_tokens = 10
+    model.zero_grad(set_to_none=True)
+    trie = TokenTrie(seqs, attachs(len(seqs)))
+    assert abs(eng.backward(model, trie, loss_fn, block_size=None) - loss_whole) < 1e-4 * max(1.0, abs(loss_whole))
+    assert eng.last_n_ranges >= 8

@@ -118,3 +118,31 @@ def test_fused_trunk_equals_hf_plugin_path():
         assert r[-1] < 1.1e-1 and r[len(r) // 2] < 3e-2, (fused, r[-1], r[len(r) // 2])
         out[fused] = (loss, {n: p.grad.float().clone() for n, p in model.named_parameters()})
     assert abs(out[True][0] - out[False][0]) < 0.01 * abs(loss_ref)
+
+
+def test_memory_bounded_ranges_on_device_and_default_budget():
+    """A trie over ``max_trie_tokens`` runs as several DFS ranges on the device: loss and gradients agree with the
+    single pass to bf16 accuracy; without an explicit budget the engine derives one from free HBM (far above this
+    trie) and does not split."""
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    from dynamictreeattn_b200.tree_training_engine import TreeTrainingEngine
+    cfg, ref, model = _models()
+    seqs = synth_trie(12, 200, (3, 2, 2), (60, 160), vocab=2048)
+    attachs = [{"w_logprobs": -1.0, "w_entropy": 0.1} for _ in seqs]
+    eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 8192)
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        trie = TokenTrie(seqs, [dict(a) for a in attachs])
+        trie.backward_permute()
+        loss = eng.backward(model, trie, tree_oracle.example_loss, block_size=2048)
+        return loss, {n: p.grad.float().clone() for n, p in model.named_parameters()}
+
+    loss1, g1 = run()
+    assert eng.last_n_ranges == 1 and eng._token_budget(True) > 100_000
+    eng.max_trie_tokens = 600
+    loss2, g2 = run()
+    assert eng.last_n_ranges >= 2
+    assert abs(loss1 - loss2) < 0.01 * abs(loss1)
+    worst = max(((g2[n] - g1[n]).norm() / (g1[n].norm() + 1e-6)).item() for n in g1)
+    assert worst < 6e-2, worst
