@@ -18,7 +18,7 @@ import torch
 _LIB_PATH = Path(os.environ.get("DTA_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libdta_b200.so")
 _lib = None
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 TILE = 128
 
 
@@ -35,6 +35,7 @@ class AttnShape(C.Structure):
         ("v_row_stride", C.c_int64), ("v_head_stride", C.c_int64),
         ("o_row_stride", C.c_int64), ("o_head_stride", C.c_int64),
         ("scale", C.c_float),
+        ("bwd_whole_tiles", C.c_int32),
     ]
 
 

@@ -47,7 +47,18 @@ def _shape(layout: TrieLayout, q, k, v, o, scale: float) -> _cabi.AttnShape:
     s.v_row_stride, s.v_head_stride = v.stride(0), v.stride(1)
     s.o_row_stride, s.o_head_stride = o.stride(0), o.stride(1)
     s.scale = float(scale)
+    s.bwd_whole_tiles = int(layout.bwd_whole_tiles(k.shape[1], _sm_count(q.device)))
     return s
+
+
+_SM_COUNT = {}
+
+
+def _sm_count(device) -> int:
+    idx = torch.device(device).index or 0
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count if torch.cuda.is_available() else 1
+    return _SM_COUNT[idx]
 
 
 def _kernel_ready(t: torch.Tensor) -> torch.Tensor:

@@ -111,7 +111,7 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
 
 // kPolyOf8: how many of every 8 exponentials of the P^T pass run on the FMA pipes (poly_exp2)
 // kDqTma: dQ tiles leave through shared memory + cp.reduce.async.bulk.tensor (TMA) instead of per-lane reds
-template <int kPolyOf8, bool kDqTma>
+template <int kPolyOf8, bool kDqTma, bool kWorkList>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -144,13 +144,25 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int widx = blockIdx.x / p.n_kv_heads;
-  if (widx >= *p.n_work) return;                          // the grid is sized for the worst-case number of chunks
-  const int4 item = p.work[widx];
-  const int jt = item.x;                                  // key tile
-  const int q_first = item.y;                             // first query tile of this CTA's chunk
-  const int n_qt = item.z;                                // query tiles in the chunk
-  const bool split = item.w != 0;                         // other CTAs hold the rest of this key tile's range
+  // kWorkList: the CTA's job comes from the device-built work list (chunks of split key tiles), else it is the whole
+  // live range of key tile k_order[blockIdx / Hkv].  The second form exists because the list costs 2-3 % of the
+  // kernel on tries that need no splitting (measured on one box with both decodes and otherwise identical code,
+  // profiles/r01/exp14_bwd_work_decode.log); the caller picks it through dta_attn_shape_t::bwd_whole_tiles.
+  int jt, q_first, n_qt;
+  bool split = false;
+  if constexpr (kWorkList) {
+    const int widx = blockIdx.x / p.n_kv_heads;
+    if (widx >= *p.n_work) return;                        // the grid is sized for the worst-case number of chunks
+    const int32_t* item = reinterpret_cast<const int32_t*>(p.work) + 4 * widx;
+    jt = item[0];                                         // key tile
+    q_first = item[1];                                    // first query tile of this CTA's chunk
+    n_qt = item[2];                                       // query tiles in the chunk
+    split = item[3] != 0;                                 // other CTAs hold the rest of this key tile's range
+  } else {
+    jt = p.k_order[blockIdx.x / p.n_kv_heads];
+    q_first = jt;
+    n_qt = p.k_qlast[jt] - jt + 1;
+  }
   const int kvh = blockIdx.x % p.n_kv_heads;
   const int k0 = jt * kT;
   const int n_iter = n_qt * p.group;
@@ -472,21 +484,23 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // partial sums of a split key tile: fp32 vector reds (16 bytes per lane; a lane owns one key row)
       float* dv_acc = p.dv_acc + (static_cast<int64_t>(k_idx) * p.n_kv_heads + kvh) * kT + ch * 64;
       float* dk_acc = p.dk_acc + (static_cast<int64_t>(k_idx) * p.n_kv_heads + kvh) * kT + ch * 64;
-#pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        uint32_t a[32], b[32];
-        tmem_ld_x32(RdV + lane_addr + ch * 64 + part * 32, a);
-        tmem_ld_x32(RdK + lane_addr + ch * 64 + part * 32, b);
+      // (rare path: a rolled loop keeps it out of the instruction cache's way -- the kernel is ~110 KB of SASS)
+      const float is = p.inv_scale;            // P^T was carried pre-multiplied by scale
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 8) {
+        uint32_t a[8], b[8];
+        tmem_ld_x8(RdV + lane_addr + ch * 64 + c, a);
+        tmem_ld_x8(RdK + lane_addr + ch * 64 + c, b);
         tmem_ld_wait();
         if (k_idx < p.n_nodes) {
-          const float is = p.inv_scale;        // P^T was carried pre-multiplied by scale
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            red_add_v4_f32(dv_acc + part * 32 + i, __uint_as_float(a[i]) * is, __uint_as_float(a[i + 1]) * is,
-                           __uint_as_float(a[i + 2]) * is, __uint_as_float(a[i + 3]) * is);
-            red_add_v4_f32(dk_acc + part * 32 + i, __uint_as_float(b[i]), __uint_as_float(b[i + 1]),
-                           __uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
-          }
+          red_add_v4_f32(dv_acc + c, __uint_as_float(a[0]) * is, __uint_as_float(a[1]) * is, __uint_as_float(a[2]) * is,
+                         __uint_as_float(a[3]) * is);
+          red_add_v4_f32(dv_acc + c + 4, __uint_as_float(a[4]) * is, __uint_as_float(a[5]) * is,
+                         __uint_as_float(a[6]) * is, __uint_as_float(a[7]) * is);
+          red_add_v4_f32(dk_acc + c, __uint_as_float(b[0]), __uint_as_float(b[1]), __uint_as_float(b[2]),
+                         __uint_as_float(b[3]));
+          red_add_v4_f32(dk_acc + c + 4, __uint_as_float(b[4]), __uint_as_float(b[5]), __uint_as_float(b[6]),
+                         __uint_as_float(b[7]));
         }
       }
     } else {
@@ -930,9 +944,13 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   float* dv_acc = reinterpret_cast<float*>(ws8 + wl.dv_acc);
   const int n_tiles_ = sh->n_pad / DTA_TILE;
   DTA_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, dq_bytes, stream));
-  const int enable_split = getenv("DTA_BWD_SPLIT") ? atoi(getenv("DTA_BWD_SPLIT")) : 1;   // 0: one CTA per key tile (A/B knob)
-  bwd_work_kernel<<<1, 1024, 0, stream>>>(meta->k_order, meta->k_qlast, n_tiles_, sm_count(), sh->n_kv_heads, enable_split, work, n_work,
-                                          k_split);
+  const int enable_split = getenv("DTA_BWD_SPLIT") ? atoi(getenv("DTA_BWD_SPLIT")) : 1;   // 0: never split (A/B knob)
+  if (sh->bwd_whole_tiles != 0 || !enable_split) {
+    DTA_CHECK_CUDA(cudaMemsetAsync(k_split, 0, static_cast<size_t>(n_tiles_) * sizeof(int32_t), stream));
+  } else {
+    bwd_work_kernel<<<1, 1024, 0, stream>>>(meta->k_order, meta->k_qlast, n_tiles_, sm_count(), sh->n_kv_heads, 1, work, n_work,
+                                            k_split);
+  }
   DTA_CHECK_CUDA(cudaGetLastError());
 
   const int64_t n_rows = static_cast<int64_t>(sh->n_pad) * sh->n_q_heads;
@@ -989,23 +1007,27 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
 
   using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                           const BwdParams);
-  static Kernel kernel = nullptr;
-  if (!kernel) {
-    // tuning knobs: DTA_BWD_POLY = share (of 8) of the exponentials computed on the FMA pipes; DTA_BWD_DQ_TMA = 0
-    // selects the per-lane red path for dQ instead of the TMA tensor reduce
+  // tuning knobs: DTA_BWD_POLY = share (of 8) of the exponentials computed on the FMA pipes; DTA_BWD_DQ_TMA = 0
+  // selects the per-lane red path for dQ instead of the TMA tensor reduce (work-list schedule only)
+  static Kernel kernels[2] = {nullptr, nullptr};          // [whole tiles, work list]
+  if (!kernels[0]) {
     const char* e = getenv("DTA_BWD_POLY");
     const int poly = e ? atoi(e) : kDefaultBwdPoly;
     const char* t = getenv("DTA_BWD_DQ_TMA");
     const bool dq_tma = t ? atoi(t) != 0 : kDefaultDqTma;
-    kernel = dq_tma ? (poly <= 0 ? tree_attn_bwd_kernel<0, true> : poly <= 2 ? tree_attn_bwd_kernel<2, true> : tree_attn_bwd_kernel<4, true>)
-                    : (poly <= 0 ? tree_attn_bwd_kernel<0, false> : poly <= 2 ? tree_attn_bwd_kernel<2, false> : tree_attn_bwd_kernel<4, false>);
-    DTA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::total));
+    kernels[0] = poly <= 0 ? tree_attn_bwd_kernel<0, true, false> : poly <= 2 ? tree_attn_bwd_kernel<2, true, false>
+                                                                              : tree_attn_bwd_kernel<4, true, false>;
+    kernels[1] = dq_tma ? (poly <= 0 ? tree_attn_bwd_kernel<0, true, true> : poly <= 2 ? tree_attn_bwd_kernel<2, true, true>
+                                                                                       : tree_attn_bwd_kernel<4, true, true>)
+                        : tree_attn_bwd_kernel<0, false, true>;
+    for (Kernel k : kernels) DTA_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::total));
   }
+  const bool whole_tiles = sh->bwd_whole_tiles != 0 || !enable_split;
+  Kernel kernel = kernels[whole_tiles ? 0 : 1];
   const int n_tiles = sh->n_pad / DTA_TILE;
   const ProfileHook hook = take_profile_hook();
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
-  (void)n_tiles;
-  kernel<<<wl.work_cap * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, tdq, p);
+  kernel<<<(whole_tiles ? n_tiles : wl.work_cap) * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, tdq, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
 

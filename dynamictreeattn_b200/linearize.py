@@ -9,9 +9,11 @@ mask ``k <= q < subtree_end[k]``.  All arrays are produced by th
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass, field
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -48,10 +50,30 @@ class TrieLayout:
     k_qlast: torch.Tensor
     pair_count: torch.Tensor     # int64 [1]  visible (q,k) pairs = sum(depth)+N
     _keep: list = field(default_factory=list, repr=False)
+    _n_pairs: Optional[int] = field(default=None, repr=False)
 
     @property
     def n_tiles(self) -> int:
         return self.n_pad // TILE
+
+    @property
+    def n_pairs(self) -> int:
+        """Visible (query, key) pairs = sum over nodes of depth + 1, from the host-side plan (no device read):
+        leaf i pushes the depths lcp[i-1] .. lens[i]-1."""
+        if self._n_pairs is None:
+            starts = [0] + list(self.lcp_lens)
+            self._n_pairs = sum((l * (l + 1) - s * (s + 1)) // 2 for l, s in zip(self.lens, starts))
+        return self._n_pairs
+
+    def bwd_whole_tiles(self, n_kv_heads: int, n_sm: int) -> bool:
+        """True when one CTA per (key tile, KV head) is provably balanced enough for the attention backward (see
+        ``dta_attn_shape_t::bwd_whole_tiles``): no key tile's query range (at most n_tiles steps per head) exceeds
+        half of an SM's share of the launch, bounded from below by pairs / 128^2 tile steps per KV head."""
+        forced = os.environ.get("DTA_BWD_SCHEDULE")          # "whole" | "worklist": tests and A/B timing
+        if forced in ("whole", "worklist"):
+            return forced == "whole"
+        share = (self.n_pairs // (TILE * TILE)) * n_kv_heads / max(n_sm, 1)
+        return self.n_tiles <= 0.5 * share
 
     def meta(self) -> _cabi.AttnMeta:
         m = _cabi.AttnMeta()

@@ -190,11 +190,17 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("heads", [(2, 1), (4, 2), (3, 3), (4, 1)])
-def test_tree_attention_fwd_bwd(name, heads):
-    """bf16 kernels vs fp32 eager masked attention on the same bf16 inputs (SURVEY §8c tolerances)."""
+def test_tree_attention_fwd_bwd(name, heads, monkeypatch):
+    """bf16 kernels vs fp32 eager masked attention on the same bf16 inputs (SURVEY §8c tolerances).  Both backward
+    schedules: the device-built work list (default for small tries; splits long-pole key tiles) and one CTA per
+    (key tile, KV head)."""
     from dynamictreeattn_b200.attention import tree_attention
     if name == "tau2_mini" and heads != (4, 2):
         pytest.skip("large case runs once")
+    if heads == (4, 1):
+        monkeypatch.setenv("DTA_BWD_SCHEDULE", "whole")
+    elif heads == (3, 3):
+        monkeypatch.setenv("DTA_BWD_SCHEDULE", "worklist")
     trie, lay = _layout(name)
     Hq, Hkv = heads
     q, k, v, do = _qkv(lay.n_nodes, Hq, Hkv)
