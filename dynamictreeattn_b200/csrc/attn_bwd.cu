@@ -145,9 +145,10 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // kWorkList: the CTA's job comes from the device-built work list (chunks of split key tiles), else it is the whole
-  // live range of key tile k_order[blockIdx / Hkv].  The second form exists because the list costs 2-3 % of the
-  // kernel on tries that need no splitting (measured on one box with both decodes and otherwise identical code,
-  // profiles/r01/exp14_bwd_work_decode.log); the caller picks it through dta_attn_shape_t::bwd_whole_tiles.
+  // live range of key tile k_order[blockIdx / Hkv].  The second form needs no list kernel, no spare CTAs and no
+  // dependent loads before the K/V fetch; earlier forms of the list decode also cost 2-4 % of the kernel through
+  // code generation alone (profiles/r01/exp14_bwd_work_decode.log).  The caller picks it through
+  // dta_attn_shape_t::bwd_whole_tiles when the launch is provably balanced without splitting.
   int jt, q_first, n_qt;
   bool split = false;
   if constexpr (kWorkList) {

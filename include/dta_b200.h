@@ -97,7 +97,7 @@ typedef struct {
   int64_t o_row_stride, o_head_stride;
   float scale; /* softmax scale, normally head_dim^-0.5 */
   /* Backward schedule.  0: work list built on the device (any trie; a key tile whose query range would be the
-   * launch's long pole is split over several CTAs).  1: one CTA per (key tile, KV head), no list -- 2-3 % faster, for
+   * launch's long pole is split over several CTAs).  1: one CTA per (key tile, KV head), no list kernel, for
    * callers that know the launch is balanced without it: n_tiles <= (pairs / 128^2) * n_kv_heads / (2 * n_sm) is
    * sufficient (pairs = visible query-key pairs, host-computable from lens / lcp).  Ignored by the forward. */
   int32_t bwd_whole_tiles;
