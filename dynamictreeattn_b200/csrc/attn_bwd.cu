@@ -635,7 +635,7 @@ static constexpr int kMinSplitTiles = 16;
 __global__ void __launch_bounds__(1024) bwd_work_kernel(const int32_t* __restrict__ k_order,
                                                         const int32_t* __restrict__ k_qlast, int n_tiles, int n_sm,
                                                         int n_kv_heads, int enable_split, int4* __restrict__ work, int32_t* __restrict__ n_work,
-                                                        int32_t* __restrict__ k_split) {
+                                                        int32_t* __restrict__ k_split, int32_t* __restrict__ split_list) {
   __shared__ int s_warp[32];
   __shared__ int s_bcast;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -702,25 +702,32 @@ __global__ void __launch_bounds__(1024) bwd_work_kernel(const int32_t* __restric
           work[base + off] = make_int4(jt, jt, n_qt, 0);
         } else {
           k_split[jt] = 1;
+          if (c == 0) split_list[base + off] = jt;     // pass 0 emits exactly one item per split tile
           const int lo = static_cast<int>(static_cast<int64_t>(c) * n_qt / parts);
           const int hi = static_cast<int>(static_cast<int64_t>(c + 1) * n_qt / parts);
           work[base + off] = make_int4(jt, jt + lo, hi - lo, 1);
         }
       }
       base += chunk_total;
+      if (c == 0 && start + static_cast<int>(blockDim.x) >= n_tiles && tid == 0) n_work[1] = base;   // number of split tiles
     }
   }
-  if (tid == 0) *n_work = base;
+  if (tid == 0) {
+    n_work[0] = base;
+    if (max_parts == 1) n_work[1] = 0;
+  }
 }
 
-// rows of split key tiles in the fp32 dK / dV accumulators ([n_pad, Hkv, 128] each, dv right behind dk)
-__device__ __forceinline__ void zero_split_rows(const int32_t* __restrict__ k_split, int n_tiles, int n_kv_heads,
-                                                float* __restrict__ dk_acc, float* __restrict__ dv_acc) {
+// rows of split key tiles in the fp32 dK / dV accumulators ([n_pad, Hkv, 128] each); split_list / n_split: the compact
+// list of those tiles (empty for every launch that needs no splitting, so the loop costs one load)
+__device__ __forceinline__ void zero_split_rows(const int32_t* __restrict__ split_list, const int32_t* __restrict__ n_split,
+                                                int n_kv_heads, float* __restrict__ dk_acc, float* __restrict__ dv_acc) {
+  const int n = *n_split;
   const int64_t per_tile = static_cast<int64_t>(kT) * n_kv_heads * (kT / 4);       // float4 per tile and buffer
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t n_thr = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int t = 0; t < n_tiles; ++t) {
-    if (!k_split[t]) continue;
+  for (int s = 0; s < n; ++s) {
+    const int t = split_list[s];
     float4* a = reinterpret_cast<float4*>(dk_acc) + t * per_tile;
     float4* b = reinterpret_cast<float4*>(dv_acc) + t * per_tile;
     for (int64_t i = tid; i < per_tile; i += n_thr) {
@@ -753,9 +760,10 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
                                                          int64_t head_stride, const float* __restrict__ lse2,
                                                          float lshift, float inv_scale_log2,
                                                          uint4* __restrict__ aug_lse, uint4* __restrict__ aug_delta,
-                                                         const int32_t* __restrict__ k_split, int n_kv_heads,
+                                                         const int32_t* __restrict__ split_list,
+                                                         const int32_t* __restrict__ n_split, int n_kv_heads,
                                                          float* __restrict__ dk_acc, float* __restrict__ dv_acc) {
-  zero_split_rows(k_split, n_pad / kT, n_kv_heads, dk_acc, dv_acc);
+  zero_split_rows(split_list, n_split, n_kv_heads, dk_acc, dv_acc);
   // half-warp per (q, h) row, 16 bytes per lane and tensor, four row pairs loaded before the first is reduced
   const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   const int64_t n_rows = static_cast<int64_t>(n_pad) * n_heads;
@@ -805,7 +813,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, int n_nodes, int n_heads,
                                                               int64_t row_stride, int64_t head_stride,
                                                               __nv_bfloat16* __restrict__ dq,
-                                                              const int32_t* __restrict__ k_split, int n_tiles,
+                                                              const int32_t* __restrict__ split_list,
+                                                              const int32_t* __restrict__ n_split,
                                                               int n_kv_heads, const float* __restrict__ dk_acc,
                                                               const float* __restrict__ dv_acc, int64_t k_row_stride,
                                                               int64_t k_head_stride, int64_t v_row_stride,
@@ -815,8 +824,9 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
     const int64_t per_tile = static_cast<int64_t>(kT) * n_kv_heads * (kT / 8);     // 8-element vectors per tile
     const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     const int64_t n_thr = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int t = 0; t < n_tiles; ++t) {
-      if (!k_split[t]) continue;
+    const int n_sp = *n_split;
+    for (int sidx = 0; sidx < n_sp; ++sidx) {
+      const int t = split_list[sidx];
       for (int64_t i = tid; i < per_tile; i += n_thr) {
         const int c = static_cast<int>(i % (kT / 8)) * 8;
         const int64_t rh = i / (kT / 8);
@@ -864,9 +874,10 @@ using namespace dta;
 
 static long long* g_bwd_trace = nullptr;
 
-// Workspace: [dq_accum fp32 | lse operand rows | delta operand rows | work items | n_work | k_split | dk_acc | dv_acc]
+// Workspace: [dq_accum fp32 | lse operand rows | delta operand rows | work items | {n_work, n_split} | k_split flags |
+//             split tile list | dk_acc | dv_acc]
 struct BwdWorkspace {
-  size_t dq, aug_lse, aug_delta, work, n_work, k_split, dk_acc, dv_acc, total;
+  size_t dq, aug_lse, aug_delta, work, n_work, k_split, split_list, dk_acc, dv_acc, total;
   int work_cap;
 };
 static BwdWorkspace bwd_workspace_layout(const dta_attn_shape_t* sh, int n_sm) {
@@ -883,6 +894,7 @@ static BwdWorkspace bwd_workspace_layout(const dta_attn_shape_t* sh, int n_sm) {
   w.work = o;      o = up(o + static_cast<size_t>(w.work_cap) * sizeof(int4));
   w.n_work = o;    o = up(o + 16);
   w.k_split = o;   o = up(o + static_cast<size_t>(n_tiles) * sizeof(int32_t));
+  w.split_list = o; o = up(o + static_cast<size_t>(n_tiles) * sizeof(int32_t));
   w.dk_acc = o;    o = up(o + dkv);
   w.dv_acc = o;    o = up(o + dkv);
   w.total = o;
@@ -892,14 +904,15 @@ static BwdWorkspace bwd_workspace_layout(const dta_attn_shape_t* sh, int n_sm) {
 extern "C" {
 
 /* debug / test only (not in the public header): the work list dta_tree_attn_bwd builds for a launch.
- * work: int32[4 * cap] {key tile, first query tile, query tiles, split}, n_work: int32[1], k_split: int32[n_tiles];
+ * work: int32[4 * cap] {key tile, first query tile, query tiles, split}, n_work: int32[2], k_split / split_list: int32[n_tiles];
  * returns the capacity the caller must provide (cap) when work == NULL. */
 int dta_debug_bwd_work_list(const int32_t* k_order, const int32_t* k_qlast, int n_tiles, int n_sm, int n_kv_heads,
-                            int32_t* work, int32_t* n_work, int32_t* k_split, dta_stream_t stream) {
+                            int32_t* work, int32_t* n_work /* [2]: items, split tiles */, int32_t* k_split,
+                            int32_t* split_list /* [n_tiles] */, dta_stream_t stream) {
   const int cap = n_tiles + (2 * n_sm + n_kv_heads - 1) / n_kv_heads + 1;
   if (work == nullptr) return cap;
   bwd_work_kernel<<<1, 1024, 0, stream>>>(k_order, k_qlast, n_tiles, n_sm, n_kv_heads, 1, reinterpret_cast<int4*>(work),
-                                          n_work, k_split);
+                                          n_work, k_split, split_list);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -941,16 +954,17 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   int4* work = reinterpret_cast<int4*>(ws8 + wl.work);
   int32_t* n_work = reinterpret_cast<int32_t*>(ws8 + wl.n_work);
   int32_t* k_split = reinterpret_cast<int32_t*>(ws8 + wl.k_split);
+  int32_t* split_list = reinterpret_cast<int32_t*>(ws8 + wl.split_list);
   float* dk_acc = reinterpret_cast<float*>(ws8 + wl.dk_acc);
   float* dv_acc = reinterpret_cast<float*>(ws8 + wl.dv_acc);
   const int n_tiles_ = sh->n_pad / DTA_TILE;
   DTA_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, dq_bytes, stream));
   const int enable_split = getenv("DTA_BWD_SPLIT") ? atoi(getenv("DTA_BWD_SPLIT")) : 1;   // 0: never split (A/B knob)
   if (sh->bwd_whole_tiles != 0 || !enable_split) {
-    DTA_CHECK_CUDA(cudaMemsetAsync(k_split, 0, static_cast<size_t>(n_tiles_) * sizeof(int32_t), stream));
+    DTA_CHECK_CUDA(cudaMemsetAsync(n_work, 0, 16, stream));                      // n_split = 0: nothing to zero or convert
   } else {
     bwd_work_kernel<<<1, 1024, 0, stream>>>(meta->k_order, meta->k_qlast, n_tiles_, sm_count(), sh->n_kv_heads, 1, work, n_work,
-                                            k_split);
+                                            k_split, split_list);
   }
   DTA_CHECK_CUDA(cudaGetLastError());
 
@@ -962,7 +976,7 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
     attn_delta_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), sh->n_nodes, sh->n_pad,
         sh->n_q_heads, sh->o_row_stride, sh->o_head_stride, lse, log2f(sh->scale), 1.0f / (sh->scale * kLog2e),
-        aug_lse, aug_delta, k_split, sh->n_kv_heads, dk_acc, dv_acc);
+        aug_lse, aug_delta, split_list, n_work + 1, sh->n_kv_heads, dk_acc, dv_acc);
     DTA_CHECK_CUDA(cudaGetLastError());
   }
 
@@ -1039,7 +1053,7 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
     if (grid > cap) grid = cap;
     attn_dq_convert_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
         dq_accum, sh->n_nodes, sh->n_q_heads, sh->q_row_stride, sh->q_head_stride, static_cast<__nv_bfloat16*>(dq),
-        k_split, n_tiles_, sh->n_kv_heads, dk_acc, dv_acc, sh->k_row_stride, sh->k_head_stride, sh->v_row_stride,
+        split_list, n_work + 1, sh->n_kv_heads, dk_acc, dv_acc, sh->k_row_stride, sh->k_head_stride, sh->v_row_stride,
         sh->v_head_stride, static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv));
     DTA_CHECK_CUDA(cudaGetLastError());
   }

@@ -266,15 +266,17 @@ def test_bwd_work_list_partitions_every_query_range(name, n_sm, n_kv):
     trie, lay = _layout(name)
     n_tiles = lay.n_pad // 128
     P = lambda t: C.c_void_p(t.data_ptr())
-    cap = raw.dta_debug_bwd_work_list(None, None, n_tiles, n_sm, n_kv, None, None, None, None)
+    cap = raw.dta_debug_bwd_work_list(None, None, n_tiles, n_sm, n_kv, None, None, None, None, None)
     work = torch.full((cap, 4), -1, dtype=torch.int32, device="cuda")
-    n_work = torch.zeros(1, dtype=torch.int32, device="cuda")
+    n_work = torch.full((2,), -1, dtype=torch.int32, device="cuda")
     k_split = torch.full((n_tiles,), -1, dtype=torch.int32, device="cuda")
+    split_list = torch.full((n_tiles,), -1, dtype=torch.int32, device="cuda")
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     assert raw.dta_debug_bwd_work_list(P(lay.k_order), P(lay.k_qlast), n_tiles, n_sm, n_kv, P(work), P(n_work),
-                                       P(k_split), st) == 0
+                                       P(k_split), P(split_list), st) == 0
     torch.cuda.synchronize()
-    n = int(n_work.item())
+    n, n_split = (int(x) for x in n_work.tolist())
+    assert sorted(split_list[:n_split].tolist()) == [t for t in range(n_tiles) if int(k_split[t]) == 1]
     assert n_tiles <= n <= cap
     items = work[:n].cpu().tolist()
     k_qlast = lay.k_qlast.cpu().tolist()
