@@ -61,8 +61,8 @@ class TrieLayout:
         """Visible (query, key) pairs = sum over nodes of depth + 1, from the host-side plan (no device read):
         leaf i pushes the depths lcp[i-1] .. lens[i]-1."""
         if self._n_pairs is None:
-            starts = [0] + list(self.lcp_lens)
-            self._n_pairs = sum((l * (l + 1) - s * (s + 1)) // 2 for l, s in zip(self.lens, starts))
+            from .trie import tree_pair_count
+            self._n_pairs = int(tree_pair_count(self.lens, self.lcp_lens))
         return self._n_pairs
 
     def bwd_whole_tiles(self, n_kv_heads: int, n_sm: int) -> bool:

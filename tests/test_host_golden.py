@@ -144,3 +144,26 @@ def test_deep_fork_chain_needs_no_recursion():
     assert sorted(order) == list(range(depth)) and len(olcps) == depth - 1
     sub = _get_subtrie(CompressedTrie(lens, lcps), set(range(0, depth, 2)))
     assert len(sub.get_order_backward()[0]) == depth // 2
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_layout_pair_count_and_backward_schedule_rule(seed):
+    """Host-side numbers the attention backward's schedule choice rests on: TrieLayout.n_pairs (closed form over
+    lens / lcp) equals the oracle's count of visible (q, k) pairs, and the whole-tile schedule is only chosen when no
+    key tile's query range can exceed half of an SM's balanced share (include/dta_b200.h, bwd_whole_tiles)."""
+    import fake_backend
+    from trie_cases import random_seqs, synth_trie
+    seqs = random_seqs(seed, 30, vocab=4, max_len=60) if seed % 2 else synth_trie(seed, 300, (3, 2), (50, 400), vocab=500)
+    trie = TokenTrie(seqs)
+    trie.backward_permute()
+    lay = fake_backend.linearize_trie(trie, "cpu")
+    lin = trie_oracle.linearize([t.tolist() for t in trie.inputs], trie.lcp_lens)
+    assert lay.n_pairs == int((lin["depth"] + 1).sum()) == int(trie_oracle.interval_mask(lin["subtree_end"]).sum())
+    assert lay.n_pairs == int(lay.pair_count.item())
+    for n_kv, n_sm in ((8, 148), (1, 148), (2, 4)):
+        whole = lay.bwd_whole_tiles(n_kv, n_sm)
+        share = (lay.n_pairs // (128 * 128)) * n_kv / n_sm
+        assert whole == (lay.n_tiles <= 0.5 * share)
+        if whole:                                         # then every tile's live range is at most half a share
+            k_qlast = lay.k_qlast.tolist()
+            assert max(k_qlast[t] - t + 1 for t in range(lay.n_tiles)) <= 0.5 * share
