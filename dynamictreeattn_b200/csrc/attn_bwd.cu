@@ -623,7 +623,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 // ------------------------------------------------------------------------------------
 // Work list of the main kernel (one CTA, once per call; n_tiles <= a few thousand).  Key tile t has
 // n_qt(t) = k_qlast[t] - t + 1 live query tiles and is one job per KV head.  With share = the (tile, head) steps an
-// SM gets when the launch is perfectly balanced, a tile longer than HALF a share,
+// SM gets when the launch is perfectly balanced: if some tile is longer than 3/4 of a share, every tile longer than
 //   L = max(kMinSplitTiles, ceil(share / 2)),   share = ceil(n_kv_heads * sum_t n_qt(t) / n_sm),
 // is cut into ceil(n_qt / L) chunks of equal size (ordering: see below); shorter tiles cannot unbalance an LPT
 // schedule by more than that and stay whole -- splitting is not free (chunks re-read K/V, leave through fp32 reds,
@@ -677,7 +677,10 @@ __global__ void __launch_bounds__(1024) bwd_work_kernel(const int32_t* __restric
   int total;
   (void)block_scan(local, total);                      // (its barriers also publish s_max)
   const int share = static_cast<int>((static_cast<int64_t>(total) * n_kv_heads + n_sm - 1) / n_sm);
-  const int split_len = enable_split ? max(kMinSplitTiles, (share + 1) / 2) : (1 << 30);
+  // split only when some tile exceeds 3/4 of a share (LPT absorbs shorter ones: splitting fan(4096, 16) at 1/2 costs
+  // 3 % schedule efficiency in tools/bwd_schedule_sim.py); chunks are then at most half a share long
+  const bool need_split = enable_split && s_max > max(kMinSplitTiles, (3 * share + 3) / 4);
+  const int split_len = need_split ? max(kMinSplitTiles, (share + 1) / 2) : (1 << 30);
   const int max_parts = (s_max + split_len - 1) / split_len;
   // Order: chunk 0 of every split tile (k_order sequence), then chunk 1 of every split tile, ..., then the unsplit
   // tiles.  Heavy items first (LPT), and the CTAs resident at the same time walk the SAME query range, which is

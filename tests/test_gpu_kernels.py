@@ -282,7 +282,7 @@ def test_bwd_work_list_partitions_every_query_range(name, n_sm, n_kv):
     k_qlast = lay.k_qlast.cpu().tolist()
     n_qt = [k_qlast[t] - t + 1 for t in range(n_tiles)]
     share = -(-sum(n_qt) * n_kv // n_sm)
-    limit = max(16, (share + 1) // 2)
+    limit = max(16, (share + 1) // 2) if max(n_qt) > max(16, (3 * share + 3) // 4) else 1 << 30
     cover = {t: [] for t in range(n_tiles)}
     for jt, q_first, cnt, split in items:
         assert 0 <= jt < n_tiles and cnt >= 1
