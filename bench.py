@@ -423,7 +423,7 @@ def run_ours(args):
             "traffic": load_ncu_traffic("tree_attn_bwd_kernel", pairs_local) if world == 1 else None,
             "traffic_note": "DRAM bytes per launch, ncu --set full (profiles/ncu_traffic.json); algorithmic minimum "
                             "~1.7 GB (q,k,v,o,dO read once, dq/dk/dv + fp32 dq accumulator written): Q/dO tiles are "
-                            "re-read per key tile from L2 (hit rate 63 %), the kernel is bound by the SM's shared-memory "
+                            "re-read per key tile from L2 (hit rate 63-68 %), the kernel is bound by the SM's shared-memory "
                             "data pipe (DESIGN.md 3.2), not by HBM",
             "peak_source": peak_src,
             "flops_per_launch": bwd_flops, "ms_per_launch": bwd_mean,
