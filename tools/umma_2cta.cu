@@ -9,6 +9,11 @@
 //   rate  : cycles per MMA for back-to-back M=256 MMAs (N = 128, 256) from the leader CTA, with and without
 //           eight warps per CTA streaming STS.128 (the interference that throttles the single-CTA kernel's
 //           dependency chain), next to the cta_group::1 M=128 N=128 rate in the same harness.
+//   mix   : the backward step's five GEMMs per iteration (S^T, dP^T SS K-major; dV TS; dQ^T SS MN/MN; dK SS K/MN; 40
+//           MMA-equivalents per SM), once as five cta_group::1 GEMMs per CTA and once as the CTA-pair version (S^T,
+//           dP^T, dV, dK as M = 256 cta_group::2 MMAs issued by the leader, dQ^T as one M = 128 MMA per CTA), with
+//           eight warps per CTA streaming STS.128: cycles per MMA-equivalent AND the shared-memory store bandwidth the
+//           stream still gets -- the quantity that bounds the real kernel (its LSU/TMA traffic is served in the gaps).
 // Every wait is bounded (mbar_wait traps); run under `timeout`.
 #include "dta_common.cuh"
 #include "dta_ptx.cuh"
@@ -48,6 +53,15 @@ __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint32_t a_lo, uin
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kSdescHi)
       : "memory");
 }
+__device__ __forceinline__ void umma_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kSdescHi)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {   // arrives on `bar` of BOTH CTAs of the pair
   const uint16_t mask = 3;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -62,8 +76,9 @@ __host__ __device__ inline float a_val(int m, int k) { return static_cast<float>
 __host__ __device__ inline float b_val(int n, int k) { return static_cast<float>(((n * 5 + k * 11) % 7) - 3); }
 
 // mode 0: probe (writes D to out[256][n_dim]);  mode 1: rate, cta_group::2;  mode 2: rate, cta_group::1 (each CTA alone)
+// mode 3: backward mix, cta_group::1 per CTA;  mode 4: backward mix as a CTA pair
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-pair_kernel(int mode, int n_dim, int iters, int interfere, float* out, long long* cycles_out) {
+pair_kernel(int mode, int n_dim, int iters, int interfere, float* out, long long* cycles_out, long long* sts_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + kABytes;
@@ -80,18 +95,19 @@ pair_kernel(int mode, int n_dim, int iters, int interfere, float* out, long long
     const int r = i / kK, k = i % kK;
     *reinterpret_cast<__nv_bfloat16*>(sA + sw_off(r, k)) = __float2bfloat16(a_val(rank * kRows + r, k));
   }
-  const int b_rows = mode == 2 ? n_dim : n_half;                      // single-CTA MMAs need all of B locally
+  const int b_rows = (mode == 2 || mode >= 3) ? 128 : n_half;         // single-CTA MMAs need all of B locally
   for (int i = threadIdx.x; i < b_rows * kK; i += blockDim.x) {
     const int r = i / kK, k = i % kK;
     *reinterpret_cast<__nv_bfloat16*>(sB + sw_off(r, k)) = __float2bfloat16(b_val((mode == 2 ? 0 : rank * n_half) + r, k));
   }
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
     *s_stop = 0;
     fence_mbar_init();
   }
   if (warp == 0) {
-    if (mode == 2) tmem_alloc(s_tmem, 512); else tmem_alloc_2cta(s_tmem, 512);
+    if (mode == 2 || mode == 3) tmem_alloc(s_tmem, 512); else tmem_alloc_2cta(s_tmem, 512);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -100,7 +116,62 @@ pair_kernel(int mode, int n_dim, int iters, int interfere, float* out, long long
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp == 0) {
+  if (mode >= 3 && warp == 0) {
+    // ---- backward-step mix.  Tiles: sA = [128][64] K-major (also read MN-major), sB likewise; K = 128 is emulated by
+    // two passes over the 64-wide tile (the operand traffic per MMA is what matters here, not the values).
+    const uint32_t kA = sdesc_lo_kmajor(smem_u32(sA)), kB = sdesc_lo_kmajor(smem_u32(sB));
+    const uint32_t nA = sdesc_lo_mnmajor(smem_u32(sA), kABytes), nB = sdesc_lo_mnmajor(smem_u32(sB), kABytes);
+    constexpr uint32_t i1_kk = make_idesc_bf16(128, 128, false, false), i1_kn = make_idesc_bf16(128, 128, false, true),
+                       i1_nn = make_idesc_bf16(128, 128, true, true);
+    constexpr uint32_t i2_kk = make_idesc_bf16(256, 128, false, false), i2_kn = make_idesc_bf16(256, 128, false, true);
+    const bool pair = mode == 4;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+        if (!pair || rank == 0) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {      // S^T
+            if (pair) umma_ss_2cta(tmem, kA + (kk & 3) * 2, kB + (kk & 3) * 2, i2_kk, kk > 0);
+            else umma_ss_lo(tmem, kA + (kk & 3) * 2, kB + (kk & 3) * 2, i1_kk, kk > 0);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {      // dP^T
+            if (pair) umma_ss_2cta(tmem + 128, kA + (kk & 3) * 2, kB + (kk & 3) * 2, i2_kk, kk > 0);
+            else umma_ss_lo(tmem + 128, kA + (kk & 3) * 2, kB + (kk & 3) * 2, i1_kk, kk > 0);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {      // dV += P^T dO   (A in TMEM, B MN-major)
+            if (pair) umma_ts_2cta(tmem + 256, tmem + (kk >> 2) * 64 + (kk & 3) * 8, nB + (kk & 3) * 128, i2_kn, kk > 0);
+            else umma_ts_lo(tmem + 256, tmem + (kk >> 2) * 64 + (kk & 3) * 8, nB + (kk & 3) * 128, i1_kn, kk > 0);
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)          // dQ^T: always one M = 128 MMA stream per CTA
+          umma_ss_lo(tmem + 128, nA + (kk & 3) * 128, nB + (kk & 3) * 128, i1_nn, kk > 0);
+        if (!pair || rank == 0) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {      // dK += dS^T Q   (A K-major, B MN-major)
+            if (pair) umma_ss_2cta(tmem + 384, kA + (kk & 3) * 2, nB + (kk & 3) * 128, i2_kn, kk > 0);
+            else umma_ss_lo(tmem + 384, kA + (kk & 3) * 2, nB + (kk & 3) * 128, i1_kn, kk > 0);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) {
+      umma_commit(bar + 1);                                   // this CTA's own cta_group::1 MMAs
+      if (pair && rank == 0) umma_commit_2cta(bar);           // the pair's MMAs, both CTAs' barriers
+      if (!pair) umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar + 1, 0);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (lane == 0) {
+      cycles_out[blockIdx.x] = t1 - t0;
+      *s_stop = 1;
+    }
+  } else if (warp == 0) {
     const bool issuer = mode == 2 || rank == 0;
     const uint32_t kA = sdesc_lo_kmajor(smem_u32(sA)), kB = sdesc_lo_kmajor(smem_u32(sB));
     const uint32_t idesc = mode == 2 ? make_idesc_bf16(128, n_dim, false, false) : make_idesc_bf16(256, n_dim, false, false);
@@ -142,6 +213,7 @@ pair_kernel(int mode, int n_dim, int iters, int interfere, float* out, long long
       for (int i = 0; i < 8; ++i)
         *reinterpret_cast<uint4*>(scratch + (((warp - 4) * 32 + lane) * 128 + ((i ^ (lane & 7)) << 4)) % 32768) = make_uint4(v, v, v, v);
     }
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(sts_out + blockIdx.x), static_cast<unsigned long long>(n) * 8 * 512);
   }
   tc_fence_before();
   __syncthreads();
@@ -161,7 +233,7 @@ pair_kernel(int mode, int n_dim, int iters, int interfere, float* out, long long
   cluster_sync_all();
   if (warp == 0) {
     tc_fence_after();
-    if (mode == 2) tmem_dealloc(tmem, 512); else tmem_dealloc_2cta(tmem, 512);
+    if (mode == 2 || mode == 3) tmem_dealloc(tmem, 512); else tmem_dealloc_2cta(tmem, 512);
   }
 }
 
@@ -174,10 +246,12 @@ int main() {
   long long* d_cyc;
   cudaMalloc(&d_out, 256 * 256 * sizeof(float));
   cudaMalloc(&d_cyc, 2 * sms * sizeof(long long));
+  long long* d_sts;
+  cudaMalloc(&d_sts, 2 * sms * sizeof(long long));
   // ---- probe
   for (int n_dim : {128, 256}) {
     cudaMemset(d_out, 0, 256 * 256 * sizeof(float));
-    pair_kernel<<<2, 384, smem>>>(0, n_dim, 1, 0, d_out, d_cyc);
+    pair_kernel<<<2, 384, smem>>>(0, n_dim, 1, 0, d_out, d_cyc, d_sts);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("probe N=%d: %s\n", n_dim, cudaGetErrorString(e)); return 1; }
     std::vector<float> h(256 * n_dim);
@@ -204,8 +278,8 @@ int main() {
                         {1, 256, 0, "cta_group::2 M=256 N=256"},          {1, 256, 1, "cta_group::2 M=256 N=256 + STS.128 x8 warps"}};
   for (const Case& c : cases) {
     const int grid = (sms / 2) * 2;
-    pair_kernel<<<grid, 384, smem>>>(c.mode, c.n, 50, c.interfere, d_out, d_cyc);
-    pair_kernel<<<grid, 384, smem>>>(c.mode, c.n, iters, c.interfere, d_out, d_cyc);
+    pair_kernel<<<grid, 384, smem>>>(c.mode, c.n, 50, c.interfere, d_out, d_cyc, d_sts);
+    pair_kernel<<<grid, 384, smem>>>(c.mode, c.n, iters, c.interfere, d_out, d_cyc, d_sts);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("rate %s: %s\n", c.name, cudaGetErrorString(e)); return 1; }
     std::vector<long long> h(grid);
@@ -216,6 +290,25 @@ int main() {
     const double flops_per_mma_per_sm = 2.0 * 128 * c.n * 16;             // per SM: 128 rows of D either way
     printf("umma_2cta rate %-46s: %.1f cycles per MMA, %.0f flop/clk/SM (8192 = peak), smem operand bytes/clk/SM %.0f\n", c.name,
            per_mma, flops_per_mma_per_sm / per_mma, (c.mode == 2 ? (128 + c.n) : (128 + c.n / 2)) * 32.0 / per_mma);
+  }
+  // ---- backward mix: five GEMMs per step, single-CTA vs CTA pair, with and without the STS stream
+  for (int mode : {3, 4}) {
+    for (int interfere : {0, 1}) {
+      const int grid = (sms / 2) * 2, mix_iters = 400;
+      pair_kernel<<<grid, 384, smem>>>(mode, 128, 20, interfere, d_out, d_cyc, d_sts);
+      cudaMemset(d_sts, 0, 2 * sms * sizeof(long long));
+      pair_kernel<<<grid, 384, smem>>>(mode, 128, mix_iters, interfere, d_out, d_cyc, d_sts);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mix mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
+      std::vector<long long> h(grid), st(grid);
+      cudaMemcpy(h.data(), d_cyc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+      cudaMemcpy(st.data(), d_sts, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long mx = 0, sts_min = 1ll << 62;
+      for (int i = 0; i < grid; ++i) { mx = h[i] > mx ? h[i] : mx; sts_min = st[i] < sts_min ? st[i] : sts_min; }
+      printf("umma_2cta mix %-14s %s: %.1f cycles per MMA-equivalent (64 = peak), STS stream gets %.1f B/clk/SM\n",
+             mode == 3 ? "cta_group::1" : "CTA pair", interfere ? "+ STS.128 x8 warps" : "alone             ",
+             static_cast<double>(mx) / (mix_iters * 40.0), interfere ? static_cast<double>(sts_min) / mx : 0.0);
+    }
   }
   return 0;
 }
