@@ -254,16 +254,38 @@ def test_chain_equals_dense_causal_sdpa():
     assert _rel(q.grad, qr.grad) < 1e-2 and _rel(k.grad, kr.grad) < 1e-2 and _rel(v.grad, vr.grad) < 1e-2
 
 
-@pytest.mark.parametrize("name", ["many_leaves", "deep_forks", "tau2_mini", "chain_300", "forest"])
+class _Meta:
+    def __init__(self, k_order, k_qlast):
+        self.k_order, self.k_qlast, self.n_pad = k_order, k_qlast, 128 * k_order.numel()
+
+
+def _synthetic_meta(n_tiles, seed):
+    """Tile metadata of no particular trie: a few very long ranges among short ones, k_order = a permutation."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n_tiles)
+    span = torch.randint(1, 40, (n_tiles,), generator=g)
+    long_ones = torch.randperm(n_tiles, generator=g)[:7]
+    span[long_ones] = n_tiles
+    k_qlast = torch.minimum(t + span - 1, torch.tensor(n_tiles - 1))
+    k_order = torch.randperm(n_tiles, generator=g)
+    return _Meta(k_order.int().cuda(), k_qlast.int().cuda())
+
+
+@pytest.mark.parametrize("name", ["many_leaves", "deep_forks", "tau2_mini", "chain_300", "forest",
+                                  "synthetic_1500_tiles", "synthetic_3000_tiles"])
 @pytest.mark.parametrize("n_sm,n_kv", [(148, 8), (148, 1), (8, 2)])
 def test_bwd_work_list_partitions_every_query_range(name, n_sm, n_kv):
     """The backward launch's work list (split query ranges for long-pole key tiles): the chunks of every key tile
     tile its live range [t, k_qlast[t]] exactly once, only tiles longer than half a balanced share are split, the
-    item count respects the bound that sizes the grid, and all chunks c of split tiles precede chunks c+1."""
+    item count respects the bound that sizes the grid, and all chunks c of split tiles precede chunks c+1.  The
+    synthetic cases have more key tiles than the list kernel has threads (several scan rounds per pass)."""
     from dynamictreeattn_b200 import _cabi
     _cabi.load()
     raw = C.CDLL(str(_cabi.lib_path()))
-    trie, lay = _layout(name)
+    if name.startswith("synthetic"):
+        lay = _synthetic_meta(int(name.split("_")[1]), seed=len(name))
+    else:
+        trie, lay = _layout(name)
     n_tiles = lay.n_pad // 128
     P = lambda t: C.c_void_p(t.data_ptr())
     cap = raw.dta_debug_bwd_work_list(None, None, n_tiles, n_sm, n_kv, None, None, None, None, None)
