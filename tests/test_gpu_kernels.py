@@ -332,6 +332,31 @@ def test_bwd_work_list_partitions_every_query_range(name, n_sm, n_kv):
     assert [jt for jt, _, _, s in items if not s] == [t for t in lay.k_order.cpu().tolist() if len(cover[t]) == 1]
 
 
+def test_backward_schedules_agree_on_bushy_16k_trie(monkeypatch):
+    """BASELINE config-5 shape with the worst long pole (64 leaves under a 252-token trunk, 16k tokens): the work-list
+    schedule (trunk tiles split into chunks, fp32 partial dK/dV through vector reds) and the whole-tile schedule give
+    the same gradients up to bf16 rounding, at Hq 16 / Hkv 8."""
+    import sys
+    from pathlib import Path as _P
+    sys.path.insert(0, str(_P(__file__).resolve().parent.parent / "tools"))
+    from attn_bench import bary
+    from dynamictreeattn_b200.attention import tree_attention
+    from dynamictreeattn_b200.linearize import linearize_trie
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    trie = TokenTrie(bary(16384, 64, 1))
+    trie.backward_permute()
+    lay = linearize_trie(trie, "cuda")
+    q, k, v, do = _qkv(lay.n_nodes, 16, 8)
+    grads = {}
+    for mode in ("whole", "worklist"):
+        monkeypatch.setenv("DTA_BWD_SCHEDULE", mode)
+        qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+        tree_attention(qq, kk, vv, lay).backward(do)
+        grads[mode] = (qq.grad, kk.grad, vv.grad)
+    for a, b in zip(grads["whole"], grads["worklist"]):
+        assert torch.isfinite(b.float()).all() and _rel(b, a) < 3e-3
+
+
 def test_constant_values_property_full_size():
     """Size-independent property at BASELINE size (tau2-16k shape, 67k trie tokens, Hq 16 / Hkv 8):
     with V == 1 every softmax row must sum to 1 -> out == 1 exactly up to bf16; and dV == sum over
