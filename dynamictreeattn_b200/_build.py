@@ -26,6 +26,7 @@ SOURCES = [
     "logprob_kernels.cu",
     "attn_fwd.cu",
     "attn_bwd.cu",
+    "attn_bwd_pair.cu",
     "layer_kernels.cu",
 ]
 

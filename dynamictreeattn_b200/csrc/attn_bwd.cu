@@ -875,6 +875,14 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
 
 using namespace dta;
 
+namespace dta {
+namespace bwd_pair {   // attn_bwd_pair.cu: experimental CTA-pair main kernel (DTA_BWD_PAIR=1)
+int launch(const void* q, const void* k, const void* v, const void* dout, const void* aug_lse, const void* aug_delta,
+           float* dq_accum, void* dk, void* dv, const dta_attn_meta_t* meta, const dta_attn_shape_t* sh, int32_t* scratch,
+           cudaEvent_t ev_start, cudaEvent_t ev_stop, cudaStream_t stream);
+}
+}  // namespace dta
+
 static long long* g_bwd_trace = nullptr;
 
 // Workspace: [dq_accum fp32 | lse operand rows | delta operand rows | work items | {n_work, n_split} | k_split flags |
@@ -963,7 +971,8 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   const int n_tiles_ = sh->n_pad / DTA_TILE;
   DTA_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, dq_bytes, stream));
   const int enable_split = getenv("DTA_BWD_SPLIT") ? atoi(getenv("DTA_BWD_SPLIT")) : 1;   // 0: never split (A/B knob)
-  if (sh->bwd_whole_tiles != 0 || !enable_split) {
+  const bool use_pair = getenv("DTA_BWD_PAIR") && atoi(getenv("DTA_BWD_PAIR")) != 0;       // experimental, see attn_bwd_pair.cu
+  if (sh->bwd_whole_tiles != 0 || !enable_split || use_pair) {
     DTA_CHECK_CUDA(cudaMemsetAsync(n_work, 0, 16, stream));                      // n_split = 0: nothing to zero or convert
   } else {
     bwd_work_kernel<<<1, 1024, 0, stream>>>(meta->k_order, meta->k_qlast, n_tiles_, sm_count(), sh->n_kv_heads, 1, work, n_work,
@@ -1044,10 +1053,17 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   Kernel kernel = kernels[whole_tiles ? 0 : 1];
   const int n_tiles = sh->n_pad / DTA_TILE;
   const ProfileHook hook = take_profile_hook();
+  if (use_pair) {
+    // whole key-tile PAIRS, no split chunks; the work-list region of the workspace is this mode's scratch
+    if ((rc = bwd_pair::launch(q, k, v, dout, aug_lse, aug_delta, dq_accum, dk, dv, meta, sh, reinterpret_cast<int32_t*>(work),
+                               hook.start, hook.stop, stream)))
+      return rc;
+  } else {
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
   kernel<<<(whole_tiles ? n_tiles : wl.work_cap) * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, tdq, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
+  }
 
   {
     const int64_t n_vec = static_cast<int64_t>(sh->n_nodes) * sh->n_q_heads * (kT / 8);
