@@ -879,7 +879,7 @@ namespace dta {
 namespace bwd_pair {   // attn_bwd_pair.cu: experimental CTA-pair main kernel (DTA_BWD_PAIR=1)
 int launch(const void* q, const void* k, const void* v, const void* dout, const void* aug_lse, const void* aug_delta,
            float* dq_accum, void* dk, void* dv, const dta_attn_meta_t* meta, const dta_attn_shape_t* sh, int32_t* scratch,
-           cudaEvent_t ev_start, cudaEvent_t ev_stop, cudaStream_t stream);
+           cudaEvent_t ev_start, cudaEvent_t ev_stop, long long* trace /* [48][2][16] or NULL */, cudaStream_t stream);
 }
 }  // namespace dta
 
@@ -927,7 +927,8 @@ int dta_debug_bwd_work_list(const int32_t* k_order, const int32_t* k_qlast, int 
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-/* debug only (not in the public header): device buffer of 48*16 int64 receiving the step timeline of CTA 0 */
+/* debug only (not in the public header): device buffer of 48*16 int64 receiving the step timeline of CTA 0
+ * (48*32 int64 in pair mode: both CTAs of cluster 0) */
 int dta_debug_set_bwd_trace(long long* buf) { g_bwd_trace = buf; return 0; }
 
 size_t dta_tree_attn_bwd_workspace_bytes(const dta_attn_shape_t* sh) {
@@ -1056,7 +1057,7 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   if (use_pair) {
     // whole key-tile PAIRS, no split chunks; the work-list region of the workspace is this mode's scratch
     if ((rc = bwd_pair::launch(q, k, v, dout, aug_lse, aug_delta, dq_accum, dk, dv, meta, sh, reinterpret_cast<int32_t*>(work),
-                               hook.start, hook.stop, stream)))
+                               hook.start, hook.stop, g_bwd_trace, stream)))
       return rc;
   } else {
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));

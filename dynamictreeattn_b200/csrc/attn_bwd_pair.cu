@@ -72,7 +72,15 @@ struct Params {
   int n_nodes, n_pad, n_tiles, n_q_heads, n_kv_heads, group;
   int64_t k_row_stride, k_head_stride, v_row_stride, v_head_stride;
   float scale_log2, inv_scale;
+  long long* trace;            // debug timeline (NULL in production): [step < 48][cluster rank][16] clock64 stamps of cluster 0
 };
+
+// per-SM clocks: stamps of the two CTAs are comparable only within a CTA
+#define DTA_PTRACE(ev)                                                                        \
+  do {                                                                                        \
+    if (p.trace != nullptr && blockIdx.x < 2 && it < 48)                                      \
+      p.trace[(it * 2 + blockIdx.x) * 16 + (ev)] = clock64();                                 \
+  } while (0)
 
 // ---- cluster / cta_group::2 wrappers (forms verified on the B200 by the two probes) ----------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -354,6 +362,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
             const uint32_t nph = st + 1 == kQStages ? stph ^ 1u : stph;
             const uint32_t not_first = it > 0 ? 1u : 0u;
             pwait_cluster(bar_p_full, it & 1);     // P^T of both CTAs written
+            if (lane == 0) DTA_PTRACE(0);
             pwait(bar_do_full, it & 1);
             tc_fence_after();
             if (elect_one()) {
@@ -363,11 +372,14 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
               umma2_commit(bar_do_empty);
             }
             __syncwarp();
+            if (lane == 0) DTA_PTRACE(13);
             if (has_next) {
               pwait(bar_q_full + nst, nph);
+              if (lane == 0) DTA_PTRACE(14);
               tc_fence_after();
               issue_st(nst);
             }
+            if (lane == 0) DTA_PTRACE(1);
             st = nst;
             stph = nph;
           }
@@ -397,6 +409,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
           const uint32_t not_first = it > 0 ? 1u : 0u;
           // own dQ^T = K^T dS^T as soon as this CTA's dS^T is in shared memory
           pwait(bar_ds_full, it & 1);
+          if (lane == 0) DTA_PTRACE(2);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
@@ -407,6 +420,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
           if (leader) {
             // dK += dS^T Q for both key tiles once both CTAs' dS^T are in place
             pwait_cluster(bar_ds_pair, it & 1);
+            if (lane == 0) DTA_PTRACE(15);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t b = nQ + st * kStage;
@@ -416,11 +430,14 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
               umma2_commit(bar_q_empty + st);
             }
             __syncwarp();
+            if (lane == 0) DTA_PTRACE(3);
             if (has_next) {
               pwait(bar_do_full, (it + 1) & 1);
               pwait_cluster(bar_r1_free, it & 1);   // R1 of both CTAs drained
+              if (lane == 0) DTA_PTRACE(4);
               tc_fence_after();
               issue_dp();
+              if (lane == 0) DTA_PTRACE(5);
             }
           }
           st = st + 1 == kQStages ? 0u : st + 1;
@@ -455,6 +472,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       const int vis_lo = k_idx - qbase, vis_hi = k_end - qbase;
 
       pwait(bar_st_full, it & 1);
+      if (threadIdx.x == 0) DTA_PTRACE(6);
       tc_fence_after();
       float pr[64];
       tmem_ld_x32(R0 + lane_addr + ch * 64, reinterpret_cast<uint32_t*>(pr));
@@ -484,8 +502,10 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(p_full_l);
+      if (threadIdx.x == 0) DTA_PTRACE(7);
 
       pwait(bar_dp_full, it & 1);
+      if (threadIdx.x == 0) DTA_PTRACE(8);
       tc_fence_after();
       uint32_t dsp[32];
       {
@@ -515,6 +535,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
         mbar_arrive(bar_ds_full);
         mbar_arrive_cluster(ds_pair_l);
       }
+      if (threadIdx.x == 0) DTA_PTRACE(9);
     }
 
     // ---- epilogue: dV, dK -> bf16 ----------------------------------------------------------
@@ -555,6 +576,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       const int head = kvh * p.group + it / n_qt;
       const int q0 = (q_first + it % n_qt) * kT;
       pwait(bar_dq_full, it & 1);
+      if (threadIdx.x == 256) DTA_PTRACE(10);
       tc_fence_after();
       float acc[128];
 #pragma unroll
@@ -563,6 +585,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(r1_free_l);
+      if (threadIdx.x == 256) DTA_PTRACE(11);
       float* stage = reinterpret_cast<float*>(smem + Smem::dq_stage) + (warp & 3) * (kDqBufs * kDqRows * 32);
       const int c0 = head * kT + ((warp & 3) << 5);
 #pragma unroll
@@ -583,6 +606,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
+      if (threadIdx.x == 256) DTA_PTRACE(12);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -649,7 +673,7 @@ __global__ void __launch_bounds__(1024) pair_order_kernel(const int32_t* __restr
 // region of the workspace, unused in this mode).  aug_lse / aug_delta / dq_accum as prepared by the caller.
 int launch(const void* q, const void* k, const void* v, const void* dout, const void* aug_lse, const void* aug_delta,
            float* dq_accum, void* dk, void* dv, const dta_attn_meta_t* meta, const dta_attn_shape_t* sh, int32_t* scratch,
-           cudaEvent_t ev_start, cudaEvent_t ev_stop, cudaStream_t stream) {
+           cudaEvent_t ev_start, cudaEvent_t ev_stop, long long* trace, cudaStream_t stream) {
   const int n_tiles = sh->n_pad / DTA_TILE;
   const int n_pairs = (n_tiles + 1) / 2;
   int32_t* first_pos = scratch;
@@ -692,6 +716,7 @@ int launch(const void* q, const void* k, const void* v, const void* dout, const 
   p.v_head_stride = sh->v_head_stride;
   p.scale_log2 = sh->scale * 1.4426950408889634f;
   p.inv_scale = 1.0f / sh->scale;
+  p.trace = trace;
 
   static bool configured = false;
   if (!configured) {

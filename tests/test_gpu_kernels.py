@@ -357,6 +357,33 @@ def test_backward_schedules_agree_on_bushy_16k_trie(monkeypatch):
         assert torch.isfinite(b.float()).all() and _rel(b, a) < 3e-3
 
 
+@pytest.mark.parametrize("name,heads", [("chain_129", (2, 1)), ("chain_300", (4, 2)), ("fan_small", (4, 2)),
+                                        ("deep_forks", (3, 3)), ("many_leaves", (4, 1)), ("forest", (4, 2)),
+                                        ("adversarial", (2, 1)), ("tau2_mini", (4, 2))])
+def test_bwd_cta_pair_kernel_parity(name, heads, monkeypatch):
+    """The experimental CTA-pair backward main kernel (cta_group::2, DTA_BWD_PAIR=1, csrc/attn_bwd_pair.cu; odd and
+    even key-tile counts, GQA groups 1-4) against the fp32 eager masked oracle at the same tolerances as the default
+    kernel, and against the default kernel's own gradients."""
+    from dynamictreeattn_b200.attention import tree_attention
+    trie, lay = _layout(name)
+    Hq, Hkv = heads
+    q, k, v, do = _qkv(lay.n_nodes, Hq, Hkv)
+    grads = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DTA_BWD_PAIR", mode)
+        qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+        tree_attention(qq, kk, vv, lay, 128 ** -0.5).backward(do)
+        grads[mode] = (qq.grad, kk.grad, vv.grad)
+    monkeypatch.setenv("DTA_BWD_PAIR", "0")
+    qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    ref, _ = tree_oracle.masked_tree_attention(qr, kr, vr, lay.subtree_end[:lay.n_nodes].long(), 128 ** -0.5)
+    ref.backward(do.float())
+    for got, want in zip(grads["1"], (qr.grad, kr.grad, vr.grad)):
+        assert torch.isfinite(got.float()).all() and _rel(got, want) < 1e-2
+    for a, b in zip(grads["0"], grads["1"]):
+        assert _rel(b, a) < 3e-3
+
+
 def test_constant_values_property_full_size():
     """Size-independent property at BASELINE size (tau2-16k shape, 67k trie tokens, Hq 16 / Hkv 8):
     with V == 1 every softmax row must sum to 1 -> out == 1 exactly up to bf16; and dV == sum over

@@ -45,6 +45,27 @@ def jobs_of(seqs, n_kv, group, sms, split, overhead):
     return [w * group + overhead for w in items for _ in range(n_kv)], n_tiles
 
 
+def pair_jobs_of(seqs, n_kv, group, overhead):
+    """CTA-pair kernel (csrc/attn_bwd_pair.cu): one job per (key tiles 2j / 2j+1, KV head) walking the UNION of the two
+    live query ranges, in the order the pairs first appear in k_order.  Returns (jobs, single-tile steps)."""
+    trie = TokenTrie(seqs)
+    trie.backward_permute()
+    lin = trie_oracle.linearize([t.tolist() for t in trie.inputs], list(trie.lcp_lens))
+    tm = trie_oracle.tile_meta(lin["subtree_end"])
+    n_tiles = len(tm["k_qlast"])
+    qlast = [int(x) for x in tm["k_qlast"]]
+    seen, items = set(), []
+    for t in (int(t) for t in tm["k_order"]):
+        j = t >> 1
+        if j in seen:
+            continue
+        seen.add(j)
+        last = max(qlast[2 * j], qlast[2 * j + 1] if 2 * j + 1 < n_tiles else 0)
+        items.append(last - 2 * j + 1)
+    single_steps = sum(qlast[t] - t + 1 for t in range(n_tiles)) * group * n_kv
+    return [w * group + overhead for w in items for _ in range(n_kv)], single_steps
+
+
 def efficiency(jobs, sms):
     heap = [0.0] * sms
     for j in jobs:
@@ -67,11 +88,16 @@ def main():
         cases[f"bary b={b}"] = bary(16384, b, max(1, math.ceil(math.log(64, b))))
     for p, b in ((1024, 64), (4096, 16), (0, 64)):
         cases[f"fan p={p} b={b}"] = trunk_fan(16384, p, b)
-    print(f"{'trie':<18s}{'tiles':>6s}{'jobs':>7s}{'eff (whole tiles)':>20s}{'jobs':>7s}{'eff (work list)':>18s}")
+    print(f"{'trie':<18s}{'tiles':>6s}{'jobs':>7s}{'eff (whole tiles)':>20s}{'jobs':>7s}{'eff (work list)':>18s}"
+          f"{'pair: steps x':>15s}{'pair: eff':>11s}")
     for name, seqs in cases.items():
         j0, n_tiles = jobs_of(seqs, a.kv_heads, a.group, a.sms, False, a.overhead)
         j1, _ = jobs_of(seqs, a.kv_heads, a.group, a.sms, True, a.overhead)
-        print(f"{name:<18s}{n_tiles:>6d}{len(j0):>7d}{efficiency(j0, a.sms):>20.3f}{len(j1):>7d}{efficiency(j1, a.sms):>18.3f}")
+        jp, single_steps = pair_jobs_of(seqs, a.kv_heads, a.group, a.overhead)
+        # a pair step does the work of two single-CTA steps on two SMs: `steps x` = SM-steps spent / SM-steps needed
+        waste = 2 * sum(j - a.overhead for j in jp) / single_steps
+        print(f"{name:<18s}{n_tiles:>6d}{len(j0):>7d}{efficiency(j0, a.sms):>20.3f}{len(j1):>7d}{efficiency(j1, a.sms):>18.3f}"
+              f"{waste:>15.3f}{efficiency(jp, a.sms // 2):>11.3f}")
 
 
 if __name__ == "__main__":
