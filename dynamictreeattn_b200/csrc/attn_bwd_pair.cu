@@ -148,8 +148,18 @@ __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* 
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// Arrival on a barrier of the pair's leader.  kClusterFences = false: the default .release.cta / .acquire.cta forms,
+// as CUTLASS's ClusterBarrier uses for the same hand-offs.  What the leader's MMAs read from the peer is SM-local state
+// of the peer (its TMEM after tcgen05.wait::st, its shared memory after the STS + fence.proxy.async), fetched by the
+// peer's own tensor core; the first version's `.release.cluster` arrive made the arriving lane wait ~1000-1600 cycles
+// on every one of the three per-step hand-offs (P^T, dS^T, R1 free) with TMA reduces and stores in flight
+// (profiles/r01/bwd_pair_trace_release_cluster.log: step period 5600 cycles against the single-CTA kernel's 4380).
+static constexpr bool kClusterFences = false;
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  if (kClusterFences)
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  else
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 // Waits of this kernel are bounded by TIME (~2 s of SM clock), not by a try count: a protocol bug must trap and
 // surface as a launch error, never hang the box.  kCluster: the barrier receives arrivals from the peer CTA
@@ -159,7 +169,7 @@ __device__ __forceinline__ void pwait_impl(uint64_t* bar, uint32_t parity) {
   long long t0 = 0;
   for (;;) {
     uint32_t ok;
-    if (kCluster)
+    if (kCluster && kClusterFences)
       asm volatile(
           "{\n\t.reg .pred P;\n\t"
           "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
