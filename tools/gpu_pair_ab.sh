@@ -1,0 +1,11 @@
+#!/bin/bash
+# First GPU visit of round 2: is the CTA-pair attention backward (DTA_BWD_PAIR=1, csrc/attn_bwd_pair.cu) faster on
+# the bench shape?  A/B on ONE box: kernel-level check + tau2 timing, both-CTA timeline, the whole GPU suite with the
+# pair kernel on, and the bench line with it off and on.  Everything lands in gpurun_out/.  ~4 minutes.
+set -u
+O=gpurun_out; mkdir -p $O
+timeout 120 python tools/bwd_pair_check.py > $O/bwd_pair_check.log 2>&1; echo "pair check exit $?"; tail -2 $O/bwd_pair_check.log | cut -c1-600
+timeout 60 python tools/bwd_pair_trace.py > $O/bwd_pair_trace.log 2>&1; head -2 $O/bwd_pair_trace.log; grep period $O/bwd_pair_trace.log
+DTA_BWD_PAIR=1 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_pair_on.log 2>&1; echo "pytest (pair on) exit $?"; tail -2 $O/pytest_gpu_pair_on.log
+python bench.py --no-cpu-baseline > $O/bench_n1_pair_off.json 2> $O/bench_n1_pair_off.err; echo "bench (pair off) exit $?"; cut -c1-160 $O/bench_n1_pair_off.json
+DTA_BWD_PAIR=1 python bench.py --no-cpu-baseline > $O/bench_n1_pair_on.json 2> $O/bench_n1_pair_on.err; echo "bench (pair on) exit $?"; cut -c1-160 $O/bench_n1_pair_on.json
