@@ -402,6 +402,10 @@ def run_ours(args):
         r = cpu_reference_run(1, 0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
+    # DTA_BWD_PAIR=1 (experimental A/B, csrc/attn_bwd_pair.cu) swaps the backward main kernel; the committed ncu
+    # capture is of the default kernel, so `traffic` is null for the pair variant
+    pair_on = os.environ.get("DTA_BWD_PAIR", "0") not in ("", "0")
+    bwd_kernel = "tree_attn_bwd_pair_kernel" if pair_on else "tree_attn_bwd_kernel"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -418,9 +422,9 @@ def run_ours(args):
             "seq_tokens_per_sec": seq_tok_global / (ms_per_step / 1e3),
         },
         "roofline": {
-            "bound": "tensor", "kernel": "tree_attn_bwd_kernel", "achieved": achieved, "peak": peak_tflops,
+            "bound": "tensor", "kernel": bwd_kernel, "achieved": achieved, "peak": peak_tflops,
             "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-            "traffic": load_ncu_traffic("tree_attn_bwd_kernel", pairs_local) if world == 1 else None,
+            "traffic": load_ncu_traffic("tree_attn_bwd_kernel", pairs_local) if world == 1 and not pair_on else None,
             "traffic_note": "DRAM bytes per launch, ncu --set full (profiles/ncu_traffic.json); algorithmic minimum "
                             "~1.7 GB (q,k,v,o,dO read once, dq/dk/dv + fp32 dq accumulator written): Q/dO tiles are "
                             "re-read per key tile from L2 (hit rate 63-68 %), the kernel is bound by the SM's shared-memory "

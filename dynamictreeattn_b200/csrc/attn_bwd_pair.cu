@@ -155,6 +155,10 @@ __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* 
 // on every one of the three per-step hand-offs (P^T, dS^T, R1 free) with TMA reduces and stores in flight
 // (profiles/r01/bwd_pair_trace_release_cluster.log: step period 5600 cycles against the single-CTA kernel's 4380).
 static constexpr bool kClusterFences = false;
+// Lane of a drain warp that sends "R1 drained" to the leader.  Lane 0 also issues the warp's TMA reduces, and its
+// arrival takes ~930 cycles to complete the leader's barrier against ~370 for the P^T arrival of a compute warp
+// (docs/next_kernels.md 1.2): round 2 tries another lane here (any lane may arrive after the __syncwarp).
+static constexpr int kDrainArriveLane = 0;
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   if (kClusterFences)
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
@@ -594,7 +598,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(r1_free_l);
+      if (lane == kDrainArriveLane) mbar_arrive_cluster(r1_free_l);
       if (threadIdx.x == 256) DTA_PTRACE(11);
       float* stage = reinterpret_cast<float*>(smem + Smem::dq_stage) + (warp & 3) * (kDqBufs * kDqRows * 32);
       const int c0 = head * kT + ((warp & 3) << 5);
