@@ -167,3 +167,43 @@ def test_layout_pair_count_and_backward_schedule_rule(seed):
         if whole:                                         # then every tile's live range is at most half a share
             k_qlast = lay.k_qlast.tolist()
             assert max(k_qlast[t] - t + 1 for t in range(lay.n_tiles)) <= 0.5 * share
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_cta_pair_schedule_premises(seed):
+    """What the CTA-pair backward kernel (csrc/attn_bwd_pair.cu) takes for granted, checked against the oracle's mask:
+    a cluster walks query tiles [2j, max(k_qlast[2j], k_qlast[2j+1])]; inside that range every query tile outside a
+    key tile's OWN live range [t, k_qlast[t]] holds no visible pair for that tile (so the fully masked steps add
+    nothing), every tile belongs to exactly one pair, and the simulator's pair order (first appearance in k_order)
+    lists every pair once."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import heapq  # noqa: F401  (bwd_schedule_sim imports it)
+    from bwd_schedule_sim import pair_jobs_of
+    from trie_cases import random_seqs, synth_trie
+    seqs = random_seqs(seed, 40, vocab=4, max_len=90) if seed % 2 else synth_trie(seed, 200, (3, 2), (60, 300), vocab=500)
+    trie = TokenTrie(seqs)
+    trie.backward_permute()
+    lin = trie_oracle.linearize([t.tolist() for t in trie.inputs], trie.lcp_lens)
+    mask = trie_oracle.interval_mask(lin["subtree_end"])            # [q, k]
+    tm = trie_oracle.tile_meta(lin["subtree_end"])
+    n = mask.shape[0]
+    n_tiles = len(tm["k_qlast"])
+    qlast = [int(x) for x in tm["k_qlast"]]
+    for j in range((n_tiles + 1) // 2):
+        last = max(qlast[2 * j], qlast[2 * j + 1] if 2 * j + 1 < n_tiles else 0)
+        for t in (2 * j, 2 * j + 1):
+            if t >= n_tiles:
+                continue
+            cols = slice(t * 128, min((t + 1) * 128, n))
+            for qt in range(n_tiles):
+                blk = mask[qt * 128:min((qt + 1) * 128, n), cols]
+                if 2 * j <= qt <= last:
+                    if not (t <= qt <= qlast[t]):
+                        assert not blk.any()                        # a masked step of the union range
+                else:
+                    assert not blk.any()                            # nothing visible outside the union range
+    jobs, single_steps = pair_jobs_of(seqs, n_kv=2, group=2, overhead=0)
+    assert len(jobs) == 2 * ((n_tiles + 1) // 2)
+    assert 2 * sum(jobs) >= single_steps == sum(qlast[t] - t + 1 for t in range(n_tiles)) * 2 * 2
