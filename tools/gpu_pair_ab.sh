@@ -6,6 +6,11 @@ set -u
 O=gpurun_out; mkdir -p $O
 timeout 120 python tools/bwd_pair_check.py > $O/bwd_pair_check.log 2>&1; echo "pair check exit $?"; tail -2 $O/bwd_pair_check.log | cut -c1-600
 timeout 60 python tools/bwd_pair_trace.py > $O/bwd_pair_trace.log 2>&1; head -2 $O/bwd_pair_trace.log; grep period $O/bwd_pair_trace.log
+# hand-off latency of the pair's barriers (arrive vs multicast commit, idle and under reduce traffic)
+mkdir -p tools/bin
+[ -x tools/bin/pair_handoff_bench ] || nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I dynamictreeattn_b200/csrc -I include \
+    tools/pair_handoff_bench.cu dynamictreeattn_b200/csrc/dta_common.cu -lcuda -o tools/bin/pair_handoff_bench
+for m in 0 1 2 3; do timeout 30 tools/bin/pair_handoff_bench $m; echo "handoff mode $m exit $?"; done > $O/pair_handoff.log 2>&1; cat $O/pair_handoff.log
 DTA_BWD_PAIR=1 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_pair_on.log 2>&1; echo "pytest (pair on) exit $?"; tail -2 $O/pytest_gpu_pair_on.log
 python bench.py --no-cpu-baseline > $O/bench_n1_pair_off.json 2> $O/bench_n1_pair_off.err; echo "bench (pair off) exit $?"; cut -c1-160 $O/bench_n1_pair_off.json
 DTA_BWD_PAIR=1 python bench.py --no-cpu-baseline > $O/bench_n1_pair_on.json 2> $O/bench_n1_pair_on.err; echo "bench (pair on) exit $?"; cut -c1-160 $O/bench_n1_pair_on.json
