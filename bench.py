@@ -171,6 +171,35 @@ def cpu_reference_run(steps: int, warmup: int, seed: int = 0):
             "sample": sample, "n_tok": n_tok}
 
 
+def dense_gpu_leg(model, seqs, attachs, dev, n_seq: int = 4):
+    """BASELINE config 2's comparison leg: the per-sequence dense-causal path (`dynamictreeattn_b200.dense.backward`,
+    the reference's dense.py:26-53 — stock HF attention, no prefix sharing) on the first `n_seq` sequences of the
+    same workload, fwd+bwd, on this GPU.  Reported in the reference's own convention, sequence tokens/s
+    (run_all.py:156-159), next to the tree path's `config.seq_tokens_per_sec`.  Never raises: a failure is recorded."""
+    try:
+        from dynamictreeattn_b200 import dense
+        ss = [seqs[i] for i in range(min(n_seq, len(seqs)))]
+        aa = [dict(attachs[i]) for i in range(len(ss))]
+        dense.backward(model, ss[:1], aa[:1], example_loss)            # warm-up (allocator, kernel selection)
+        model.zero_grad(set_to_none=True)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dense.backward(model, ss, aa, example_loss)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        toks = sum(int(s.numel()) for s in ss)
+        return {"value": toks / (ms / 1e3), "unit": "sequence tokens/s", "ms": ms, "sequences": len(ss),
+                "sequence_tokens": toks, "attn_implementation": str(getattr(model.config, "_attn_implementation", "?")),
+                "sample": f"first {len(ss)} of {len(seqs)} sequences of the bench trie, one causal fwd+bwd each"}
+    except Exception as e:  # noqa: BLE001  (a comparison leg must not take the bench line down)
+        return {"value": None, "unit": "sequence tokens/s", "error": f"{type(e).__name__}: {str(e)[:200]}"}
+    finally:
+        model.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -397,6 +426,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    peak_mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    dense_line = None
+    if world == 1 and not args.no_dense_baseline:
+        dense_line = dense_gpu_leg(model, seqs, attachs, dev)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(1, 0)
@@ -435,11 +468,12 @@ def run_ours(args):
             "attn_share_of_step": attn_share,
         },
         "cpu_baseline": cpu,
+        "dense_baseline": dense_line,
         "e2e": {"value": n_tok_global / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+        "peak_mem_gb": peak_mem_gb,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -453,6 +487,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

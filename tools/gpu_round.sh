@@ -11,7 +11,7 @@ python tools/attn_bench.py --case tau2 > gpurun_out/attn_bench.json 2>&1; cat gp
 python tools/step_profile.py > gpurun_out/step_profile.log 2>&1; head -40 gpurun_out/step_profile.log
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
-    python bench.py --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu list exit $?"
+    python bench.py --no-cpu-baseline --no-dense-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu list exit $?"
 python tools/launch_summary.py gpurun_out/launches.csv > gpurun_out/launch_summary.txt 2>&1; head -30 gpurun_out/launch_summary.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tree_attn_.*_kernel -c 2 -f -o gpurun_out/attn_full \
     python tools/attn_bench.py --case tau2 --iters 1 > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
