@@ -26,6 +26,7 @@
 #include "dta_ptx.cuh"
 #include "../../include/dta_b200.h"
 #include <climits>
+#include <cstdlib>
 
 namespace dta {
 namespace bwd_pair {
@@ -72,6 +73,7 @@ struct Params {
   int n_nodes, n_pad, n_tiles, n_q_heads, n_kv_heads, group;
   int64_t k_row_stride, k_head_stride, v_row_stride, v_head_stride;
   float scale_log2, inv_scale;
+  int drain_lane;
   long long* trace;            // debug timeline (NULL in production): [step < 48][cluster rank][16] clock64 stamps of cluster 0
 };
 
@@ -155,10 +157,10 @@ __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* 
 // on every one of the three per-step hand-offs (P^T, dS^T, R1 free) with TMA reduces and stores in flight
 // (profiles/r01/bwd_pair_trace_release_cluster.log: step period 5600 cycles against the single-CTA kernel's 4380).
 static constexpr bool kClusterFences = false;
-// Lane of a drain warp that sends "R1 drained" to the leader.  Lane 0 also issues the warp's TMA reduces, and its
-// arrival takes ~930 cycles to complete the leader's barrier against ~370 for the P^T arrival of a compute warp
-// (docs/next_kernels.md 1.2): round 2 tries another lane here (any lane may arrive after the __syncwarp).
-static constexpr int kDrainArriveLane = 0;
+// Params::drain_lane: lane of a drain warp that sends "R1 drained" to the leader.  Lane 0 also issues the warp's TMA
+// reduces, and its arrival takes ~930 cycles to complete the leader's barrier against ~370 for the P^T arrival of a
+// compute warp (docs/next_kernels.md 1.2); DTA_PAIR_DRAIN_LANE picks another lane for the A/B (any lane may arrive
+// after the __syncwarp).  Default 0 = the measured configuration.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   if (kClusterFences)
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
@@ -196,6 +198,8 @@ __device__ __forceinline__ void pwait_impl(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void pwait(uint64_t* bar, uint32_t parity) { pwait_impl<false>(bar, parity); }
 __device__ __forceinline__ void pwait_cluster(uint64_t* bar, uint32_t parity) { pwait_impl<true>(bar, parity); }
 
+// kPolyOf8: how many of every 8 exponentials of the P^T pass run on the FMA pipes (poly_exp2), as in attn_bwd.cu
+template <int kPolyOf8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __grid_constant__ CUtensorMap tmap_q128,
                           const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -497,11 +501,15 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
         if (hf == 1) tmem_ld_wait();
         if (!partial) {
 #pragma unroll
-          for (int c = hf * 32; c < hf * 32 + 32; ++c) pr[c] = fast_exp2(pr[c] * p.scale_log2);
+          for (int c = hf * 32; c < hf * 32 + 32; ++c) {
+            const float x = pr[c] * p.scale_log2;
+            pr[c] = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
+          }
         } else {
 #pragma unroll
           for (int c = hf * 32; c < hf * 32 + 32; ++c) {
-            const float v = fast_exp2(pr[c] * p.scale_log2);
+            const float x = pr[c] * p.scale_log2;
+            const float v = exp2_slot_on_fma<kPolyOf8>(c) ? poly_exp2(x) : fast_exp2(x);
             pr[c] = (c >= vis_lo && c < vis_hi) ? v : 0.f;
           }
         }
@@ -598,7 +606,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == kDrainArriveLane) mbar_arrive_cluster(r1_free_l);
+      if (lane == p.drain_lane) mbar_arrive_cluster(r1_free_l);
       if (threadIdx.x == 256) DTA_PTRACE(11);
       float* stage = reinterpret_cast<float*>(smem + Smem::dq_stage) + (warp & 3) * (kDqBufs * kDqRows * 32);
       const int c0 = head * kT + ((warp & 3) << 5);
@@ -731,15 +739,22 @@ int launch(const void* q, const void* k, const void* v, const void* dout, const 
   p.scale_log2 = sh->scale * 1.4426950408889634f;
   p.inv_scale = 1.0f / sh->scale;
   p.trace = trace;
+  const char* dl = getenv("DTA_PAIR_DRAIN_LANE");
+  p.drain_lane = dl ? (atoi(dl) & 31) : 0;
 
+  using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                          const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+  static const Kernel kernels[3] = {tree_attn_bwd_pair_kernel<0>, tree_attn_bwd_pair_kernel<2>, tree_attn_bwd_pair_kernel<4>};
   static bool configured = false;
   if (!configured) {
-    DTA_CHECK_CUDA(cudaFuncSetAttribute(tree_attn_bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    for (Kernel kf : kernels) DTA_CHECK_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     configured = true;
   }
+  const char* pe = getenv("DTA_BWD_POLY");                 // same tuning knob as the single-CTA kernel; default 0
+  const int poly = pe ? atoi(pe) : 0;
+  const Kernel kernel = kernels[poly <= 0 ? 0 : poly <= 2 ? 1 : 2];
   if (ev_start) DTA_CHECK_CUDA(cudaEventRecord(ev_start, stream));
-  tree_attn_bwd_pair_kernel<<<2 * n_pairs * sh->n_kv_heads, kThreads, Smem::total, stream>>>(tq64, tq128, tk, tv, tdo64, tdo128, tdq,
-                                                                                          taug_l, taug_d, p);
+  kernel<<<2 * n_pairs * sh->n_kv_heads, kThreads, Smem::total, stream>>>(tq64, tq128, tk, tv, tdo64, tdo128, tdq, taug_l, taug_d, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (ev_stop) DTA_CHECK_CUDA(cudaEventRecord(ev_stop, stream));
   return DTA_OK;

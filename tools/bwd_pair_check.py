@@ -3,6 +3,7 @@ single-CTA kernel on the same inputs: dq / dk / dv differences, then kernel time
 
     python tools/bwd_pair_check.py              # every case in order, stopping at the first failure
     python tools/bwd_pair_check.py --case NAME  # one case
+    python tools/bwd_pair_check.py --sweep tau2 # kernel times of the pair variants (poly share x drain-arrival lane)
 
 Cases grow from one key-tile pair to the bench shape so that the first failing line localises the bug.
 """
@@ -98,11 +99,46 @@ def run_case(name, Hq=16, Hkv=8, iters=3):
     return ok
 
 
+def sweep(name="tau2", Hq=16, Hkv=8, iters=5):
+    """Kernel time of the pair variants (DTA_BWD_POLY x DTA_PAIR_DRAIN_LANE) next to the single-CTA kernel, one trie."""
+    import torch
+    from dynamictreeattn_b200 import attention
+    from dynamictreeattn_b200.attention import tree_attention
+    from dynamictreeattn_b200.linearize import linearize_trie
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    trie = TokenTrie(seqs_for(name))
+    trie.backward_permute()
+    lay = linearize_trie(trie, "cuda")
+    N, P = lay.n_nodes, int(lay.pair_count.item())
+    g = torch.Generator(device="cuda").manual_seed(0)
+    mk = lambda h: torch.randn(N, h, 128, device="cuda", generator=g).bfloat16().requires_grad_(True)   # noqa: E731
+    q, k, v = mk(Hq), mk(Hkv), mk(Hkv)
+    do = torch.randn(N, Hq, 128, device="cuda", generator=g).bfloat16()
+    for pair, poly, lane in [("0", "0", "0")] + [("1", po, la) for po in ("0", "2", "4") for la in ("0", "1")]:
+        os.environ.update(DTA_BWD_PAIR=pair, DTA_BWD_POLY=poly, DTA_PAIR_DRAIN_LANE=lane)
+        tree_attention(q, k, v, lay).backward(do)
+        attention.PROFILE = []
+        for _ in range(iters):
+            q.grad = k.grad = v.grad = None
+            tree_attention(q, k, v, lay).backward(do)
+        torch.cuda.synchronize()
+        ms = statistics.median(a.elapsed_time(b) for kind, a, b in attention.PROFILE if kind == "bwd")
+        attention.PROFILE = None
+        print(json.dumps({"case": name, "pair": int(pair), "poly_of_8": int(poly), "drain_lane": int(lane),
+                          "bwd_ms": round(ms, 3), "bwd_tflops": round(10 * P * Hq * 128 / ms / 1e9, 1)}), flush=True)
+    for key in ("DTA_BWD_PAIR", "DTA_BWD_POLY", "DTA_PAIR_DRAIN_LANE"):
+        os.environ.pop(key, None)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default=None)
+    ap.add_argument("--sweep", default=None, help="time the pair variants on this case (e.g. tau2, chain_16384) and exit")
     ap.add_argument("--stop-on-fail", type=int, default=1)
     args = ap.parse_args()
+    if args.sweep:
+        sweep(args.sweep)
+        return
     if args.case:
         sys.exit(0 if run_case(args.case) else 1)
     for name in CASES:       # in one process: after a trap the CUDA context is gone anyway, so stop at the first failure

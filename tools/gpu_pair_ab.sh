@@ -5,6 +5,7 @@
 set -u
 O=gpurun_out; mkdir -p $O
 timeout 120 python tools/bwd_pair_check.py > $O/bwd_pair_check.log 2>&1; echo "pair check exit $?"; tail -2 $O/bwd_pair_check.log | cut -c1-600
+timeout 90 python tools/bwd_pair_check.py --sweep tau2 > $O/bwd_pair_sweep.log 2>&1; cat $O/bwd_pair_sweep.log | cut -c1-200
 timeout 60 python tools/bwd_pair_trace.py > $O/bwd_pair_trace.log 2>&1; head -2 $O/bwd_pair_trace.log; grep period $O/bwd_pair_trace.log
 # hand-off latency of the pair's barriers (arrive vs multicast commit, idle and under reduce traffic)
 mkdir -p tools/bin
