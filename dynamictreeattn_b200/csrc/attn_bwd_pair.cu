@@ -73,6 +73,10 @@ struct Params {
   int n_nodes, n_pad, n_tiles, n_q_heads, n_kv_heads, group;
   int64_t k_row_stride, k_head_stride, v_row_stride, v_head_stride;
   float scale_log2, inv_scale;
+  // lane of a drain warp that sends "R1 drained" to the leader.  Lane 0 also issues the warp's TMA reduces, and its
+  // arrival takes ~930 cycles to complete the leader's barrier against ~370 for the P^T arrival of a compute warp
+  // (docs/next_kernels.md 1.2); DTA_PAIR_DRAIN_LANE picks another lane for the A/B (any lane may arrive after the
+  // __syncwarp).  Default 0 = the measured configuration.
   int drain_lane;
   long long* trace;            // debug timeline (NULL in production): [step < 48][cluster rank][16] clock64 stamps of cluster 0
 };
@@ -155,12 +159,9 @@ __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* 
 // of the peer (its TMEM after tcgen05.wait::st, its shared memory after the STS + fence.proxy.async), fetched by the
 // peer's own tensor core; the first version's `.release.cluster` arrive made the arriving lane wait ~1000-1600 cycles
 // on every one of the three per-step hand-offs (P^T, dS^T, R1 free) with TMA reduces and stores in flight
-// (profiles/r01/bwd_pair_trace_release_cluster.log: step period 5600 cycles against the single-CTA kernel's 4380).
+// (profiles/r01/bwd_pair_trace_release_cluster.log: step period 5735 cycles against the single-CTA kernel's 4356;
+// 4074 with this form, profiles/r01/bwd_pair_trace.log).
 static constexpr bool kClusterFences = false;
-// Params::drain_lane: lane of a drain warp that sends "R1 drained" to the leader.  Lane 0 also issues the warp's TMA
-// reduces, and its arrival takes ~930 cycles to complete the leader's barrier against ~370 for the P^T arrival of a
-// compute warp (docs/next_kernels.md 1.2); DTA_PAIR_DRAIN_LANE picks another lane for the A/B (any lane may arrive
-// after the __syncwarp).  Default 0 = the measured configuration.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   if (kClusterFences)
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
@@ -169,7 +170,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
 }
 // Waits of this kernel are bounded by TIME (~2 s of SM clock), not by a try count: a protocol bug must trap and
 // surface as a launch error, never hang the box.  kCluster: the barrier receives arrivals from the peer CTA
-// (acquire at cluster scope).
+// (acquire at cluster scope when kClusterFences, else the default form like every other wait).
 template <bool kCluster>
 __device__ __forceinline__ void pwait_impl(uint64_t* bar, uint32_t parity) {
   long long t0 = 0;
