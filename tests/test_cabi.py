@@ -58,3 +58,24 @@ def test_product_never_imports_oracle():
     pkg = ROOT / "dynamictreeattn_b200"
     for p in pkg.rglob("*.py"):
         assert not re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), flags=re.M), p
+
+
+def test_bench_dense_leg_records_failure_instead_of_raising():
+    """bench.py's dense-causal comparison leg runs after the primary numbers are taken and must never take the bench
+    line down: without a GPU the product log-prob op refuses to run (no CPU fallback) and the leg reports that."""
+    import sys
+    from pathlib import Path
+    import torch
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("failure path is the CPU-only one")
+    cfg = Qwen3Config(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=1, num_attention_heads=2,
+                      num_key_value_heads=1, head_dim=16)
+    model = Qwen3ForCausalLM(cfg)
+    seqs = [torch.randint(0, 64, (12,)), torch.randint(0, 64, (9,))]
+    out = bench.dense_gpu_leg(model, seqs, [dict(bench.ATTACH) for _ in seqs], torch.device("cpu"))
+    assert out["value"] is None and "error" in out and out["unit"] == "sequence tokens/s"
+    assert all(p.grad is None for p in model.parameters())
