@@ -437,7 +437,9 @@ def run_ours(args):
 
     # DTA_BWD_PAIR=1 (experimental A/B, csrc/attn_bwd_pair.cu) swaps the backward main kernel; the committed ncu
     # capture is of the default kernel, so `traffic` is null for the pair variant
-    pair_on = os.environ.get("DTA_BWD_PAIR", "0") not in ("", "0")
+    pair_env = os.environ.get("DTA_BWD_PAIR", "0")
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    pair_on = layout.bwd_whole_tiles(cfg.num_key_value_heads, n_sm) if pair_env == "auto" else pair_env not in ("", "0")
     bwd_kernel = "tree_attn_bwd_pair_kernel" if pair_on else "tree_attn_bwd_kernel"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

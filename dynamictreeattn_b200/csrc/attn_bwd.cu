@@ -35,6 +35,7 @@
 #include "../../include/dta_b200.h"
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace dta {
 
@@ -972,7 +973,10 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   const int n_tiles_ = sh->n_pad / DTA_TILE;
   DTA_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, dq_bytes, stream));
   const int enable_split = getenv("DTA_BWD_SPLIT") ? atoi(getenv("DTA_BWD_SPLIT")) : 1;   // 0: never split (A/B knob)
-  const bool use_pair = getenv("DTA_BWD_PAIR") && atoi(getenv("DTA_BWD_PAIR")) != 0;       // experimental, see attn_bwd_pair.cu
+  // experimental CTA-pair main kernel (attn_bwd_pair.cu): "1" = always, "auto" = for launches the caller marked balanced
+  // (bwd_whole_tiles; the pair kernel has no split chunks and pairing wastes 22-33 % of the steps on bushy tries)
+  const char* pair_env = getenv("DTA_BWD_PAIR");
+  const bool use_pair = pair_env && (strcmp(pair_env, "auto") == 0 ? sh->bwd_whole_tiles != 0 : atoi(pair_env) != 0);
   if (sh->bwd_whole_tiles != 0 || !enable_split || use_pair) {
     DTA_CHECK_CUDA(cudaMemsetAsync(n_work, 0, 16, stream));                      // n_split = 0: nothing to zero or convert
   } else {

@@ -14,4 +14,4 @@ mkdir -p tools/bin
 for m in 0 1 2 3; do timeout 30 tools/bin/pair_handoff_bench $m; echo "handoff mode $m exit $?"; done > $O/pair_handoff.log 2>&1; cat $O/pair_handoff.log
 DTA_BWD_PAIR=1 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_pair_on.log 2>&1; echo "pytest (pair on) exit $?"; tail -2 $O/pytest_gpu_pair_on.log
 python bench.py --no-cpu-baseline > $O/bench_n1_pair_off.json 2> $O/bench_n1_pair_off.err; echo "bench (pair off) exit $?"; cut -c1-160 $O/bench_n1_pair_off.json
-DTA_BWD_PAIR=1 python bench.py --no-cpu-baseline > $O/bench_n1_pair_on.json 2> $O/bench_n1_pair_on.err; echo "bench (pair on) exit $?"; cut -c1-160 $O/bench_n1_pair_on.json
+DTA_BWD_PAIR=auto python bench.py --no-cpu-baseline > $O/bench_n1_pair_auto.json 2> $O/bench_n1_pair_auto.err; echo "bench (pair auto) exit $?"; cut -c1-160 $O/bench_n1_pair_auto.json
