@@ -27,6 +27,7 @@
 #include "../../include/dta_b200.h"
 #include <climits>
 #include <cstdlib>
+#include <cstring>
 
 namespace dta {
 namespace bwd_pair {
@@ -78,6 +79,7 @@ struct Params {
   // (docs/next_kernels.md 1.2); DTA_PAIR_DRAIN_LANE picks another lane for the A/B (any lane may arrive after the
   // __syncwarp).  Default 0 = the measured configuration.
   int drain_lane;
+  int handoff_commit;          // 1: the three hand-offs to the leader use commit_signal_leader instead of a remote arrive
   long long* trace;            // debug timeline (NULL in production): [step < 48][cluster rank][16] clock64 stamps of cluster 0
 };
 
@@ -129,6 +131,17 @@ __device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint3
 // arrives on `bar` (same shared-memory offset) of BOTH CTAs of the pair when the issuing thread's MMAs retire
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
   const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// Same instruction used as a pure SIGNAL to the leader (mask 1) by a thread that has no MMA outstanding: the commit
+// path delivered the leader's barriers to the peer within ~20 cycles where a remote mbarrier.arrive took 370-930
+// (docs/next_kernels.md 1.2).  UNTESTED variant (DTA_PAIR_HANDOFF=commit): whether a thread of the NON-leader CTA may
+// issue it is what tools/pair_handoff_bench.cu mode 3 finds out first.
+__device__ __forceinline__ void commit_signal_leader(uint64_t* bar) {
+  const uint16_t mask = 1;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
                "h"(mask)
@@ -524,7 +537,9 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(p_full_l);
+      if (lane == 0) {
+        if (p.handoff_commit) commit_signal_leader(bar_p_full); else mbar_arrive_cluster(p_full_l);
+      }
       if (threadIdx.x == 0) DTA_PTRACE(7);
 
       pwait(bar_dp_full, it & 1);
@@ -556,7 +571,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_ds_full);
-        mbar_arrive_cluster(ds_pair_l);
+        if (p.handoff_commit) commit_signal_leader(bar_ds_pair); else mbar_arrive_cluster(ds_pair_l);
       }
       if (threadIdx.x == 0) DTA_PTRACE(9);
     }
@@ -607,7 +622,9 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == p.drain_lane) mbar_arrive_cluster(r1_free_l);
+      if (lane == p.drain_lane) {
+        if (p.handoff_commit) commit_signal_leader(bar_r1_free); else mbar_arrive_cluster(r1_free_l);
+      }
       if (threadIdx.x == 256) DTA_PTRACE(11);
       float* stage = reinterpret_cast<float*>(smem + Smem::dq_stage) + (warp & 3) * (kDqBufs * kDqRows * 32);
       const int c0 = head * kT + ((warp & 3) << 5);
@@ -742,6 +759,8 @@ int launch(const void* q, const void* k, const void* v, const void* dout, const 
   p.trace = trace;
   const char* dl = getenv("DTA_PAIR_DRAIN_LANE");
   p.drain_lane = dl ? (atoi(dl) & 31) : 0;
+  const char* ho = getenv("DTA_PAIR_HANDOFF");
+  p.handoff_commit = ho && strcmp(ho, "commit") == 0 ? 1 : 0;
 
   using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                           const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);

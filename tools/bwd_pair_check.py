@@ -114,8 +114,11 @@ def sweep(name="tau2", Hq=16, Hkv=8, iters=5):
     mk = lambda h: torch.randn(N, h, 128, device="cuda", generator=g).bfloat16().requires_grad_(True)   # noqa: E731
     q, k, v = mk(Hq), mk(Hkv), mk(Hkv)
     do = torch.randn(N, Hq, 128, device="cuda", generator=g).bfloat16()
-    for pair, poly, lane in [("0", "0", "0")] + [("1", po, la) for po in ("0", "2", "4") for la in ("0", "1")]:
-        os.environ.update(DTA_BWD_PAIR=pair, DTA_BWD_POLY=poly, DTA_PAIR_DRAIN_LANE=lane)
+    variants = [("0", "0", "0", "arrive")] + [("1", po, la, "arrive") for po in ("0", "2", "4") for la in ("0", "1")]
+    if os.environ.get("PAIR_SWEEP_COMMIT") == "1":           # only once tools/pair_handoff_bench mode 3 has passed: may trap
+        variants += [("1", "0", "0", "commit"), ("1", "2", "0", "commit")]
+    for pair, poly, lane, handoff in variants:
+        os.environ.update(DTA_BWD_PAIR=pair, DTA_BWD_POLY=poly, DTA_PAIR_DRAIN_LANE=lane, DTA_PAIR_HANDOFF=handoff)
         tree_attention(q, k, v, lay).backward(do)
         attention.PROFILE = []
         for _ in range(iters):
@@ -124,9 +127,9 @@ def sweep(name="tau2", Hq=16, Hkv=8, iters=5):
         torch.cuda.synchronize()
         ms = statistics.median(a.elapsed_time(b) for kind, a, b in attention.PROFILE if kind == "bwd")
         attention.PROFILE = None
-        print(json.dumps({"case": name, "pair": int(pair), "poly_of_8": int(poly), "drain_lane": int(lane),
+        print(json.dumps({"case": name, "pair": int(pair), "poly_of_8": int(poly), "drain_lane": int(lane), "handoff": handoff,
                           "bwd_ms": round(ms, 3), "bwd_tflops": round(10 * P * Hq * 128 / ms / 1e9, 1)}), flush=True)
-    for key in ("DTA_BWD_PAIR", "DTA_BWD_POLY", "DTA_PAIR_DRAIN_LANE"):
+    for key in ("DTA_BWD_PAIR", "DTA_BWD_POLY", "DTA_PAIR_DRAIN_LANE", "DTA_PAIR_HANDOFF"):
         os.environ.pop(key, None)
 
 
