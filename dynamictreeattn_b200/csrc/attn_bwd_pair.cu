@@ -168,7 +168,7 @@ __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* 
       : "memory");
 }
 // Arrival on a barrier of the pair's leader.  kClusterFences = false: the default .release.cta / .acquire.cta forms,
-// as CUTLASS's ClusterBarrier uses for the same hand-offs.  What the leader's MMAs read from the peer is SM-local state
+// as CUTLASS uses for the same hand-offs (ClusterBarrier::arrive, umma_arrive_2x1SM_sm0 in cutlass/arch/barrier.h).  What the leader's MMAs read from the peer is SM-local state
 // of the peer (its TMEM after tcgen05.wait::st, its shared memory after the STS + fence.proxy.async), fetched by the
 // peer's own tensor core; the first version's `.release.cluster` arrive made the arriving lane wait ~1000-1600 cycles
 // on every one of the three per-step hand-offs (P^T, dS^T, R1 free) with TMA reduces and stores in flight
