@@ -18,7 +18,7 @@ import torch
 _LIB_PATH = Path(os.environ.get("DTA_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libdta_b200.so")
 _lib = None
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 TILE = 128
 
 
@@ -59,10 +59,10 @@ SIGNATURES = {
     "dta_profile_next_attn": (_I, [_P, _P]),
     "dta_tree_attn_bwd_workspace_bytes": (_Z, [C.POINTER(AttnShape)]),
     "dta_tree_attn_bwd": (_I, [_P] * 9 + [C.POINTER(AttnMeta), C.POINTER(AttnShape), _P, _P]),
-    "dta_logprob_row_stats": (_I, [_P, _I, _L, _L, _L, _F, _P, _P]),
+    "dta_logprob_row_stats": (_I, [_P, _I, _L, _L, _L, _F, _P, _L, _P, _P]),
     "dta_logprob_gather_labels": (_I, [_P, _I, _L, _L, _F, _P, _P, _L, _L, _P, _L, _P]),
-    "dta_logprob_finalize": (_I, [_P, _I, _L, _P, _P, _P, _P]),
-    "dta_logprob_bwd": (_I, [_P, _I, _L, _L, _L, _F, _P, _P, _P, _P, _P, _L, _P]),
+    "dta_logprob_finalize": (_I, [_P, _I, _L, _L, _P, _P, _P, _P]),
+    "dta_logprob_bwd": (_I, [_P, _I, _L, _L, _L, _F, _P, _P, _P, _P, _P, _L, _P, _L, _P]),
     "dta_logprob_bwd_scatter": (_I, [_P, _I, _L, _L, _F, _P, _P, _P, _L, _L, _P]),
     "dta_logprob_rowsum_grad": (_I, [_P, _P, _L, _P, _P]),
     "dta_rmsnorm_fwd": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),

@@ -76,13 +76,22 @@ template <> struct Vec<float> {
 template <typename T>
 __global__ void __launch_bounds__(kRowThreads) row_stats_kernel(const T* __restrict__ logits, int64_t n_rows,
                                                                int64_t n_cols, int64_t row_stride, float inv_temp,
+                                                               const int64_t* __restrict__ labels, int64_t vocab_start,
                                                                float* __restrict__ stats) {
   constexpr int V = Vec<T>::N;
   constexpr int U = 4;  // vectors in flight per thread
   __shared__ RowStat s_part[kRowThreads / 32];
+  __shared__ float s_xl;
   const float c = inv_temp * kLog2e;
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
     const T* p = logits + row * row_stride;
+    // the row's label logit (one label per row): requested first by one thread of the LAST warp, so the dependent
+    // load is in flight under the whole row pass and thread 0 finds it in shared memory after the block reduction
+    float xl = 0.f;
+    if (labels != nullptr && threadIdx.x == kRowThreads - 1) {
+      const int64_t lc = labels[row] - vocab_start;
+      if (lc >= 0 && lc < n_cols) xl = Vec<T>::get(p + lc) * inv_temp;
+    }
     RowStat st{-INFINITY, 0.f, 0.f};
     const bool vec_ok = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
     const int64_t n_vec = vec_ok ? n_cols / V : 0;
@@ -124,6 +133,7 @@ __global__ void __launch_bounds__(kRowThreads) row_stats_kernel(const T* __restr
       st = merge(st, other);
     }
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = st;
+    if (threadIdx.x == kRowThreads - 1) s_xl = xl;
     __syncthreads();
     if (threadIdx.x < 32) {
       RowStat r = threadIdx.x < kRowThreads / 32 ? s_part[threadIdx.x] : RowStat{-INFINITY, 0.f, 0.f};
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(kRowThreads) row_stats_kernel(const T* __restr
         r = merge(r, other);
       }
       if (threadIdx.x == 0)
-        reinterpret_cast<float4*>(stats)[row] = make_float4(r.m, r.s, r.t * inv_temp, 0.f);
+        reinterpret_cast<float4*>(stats)[row] = make_float4(r.m, r.s, r.t * inv_temp, s_xl);
     }
     __syncthreads();
   }
@@ -155,16 +165,16 @@ __global__ void gather_labels_kernel(const T* __restrict__ logits, int64_t n_col
   }
 }
 
-__global__ void finalize_kernel(const float4* __restrict__ stats_all, int world, int64_t n_rows,
-                                float* __restrict__ logz, float* __restrict__ entropy,
-                                float* __restrict__ x_label_sum) {
+__global__ void finalize_kernel(const float4* __restrict__ stats_all, int world, int64_t world_stride4,
+                                int64_t n_rows, float* __restrict__ logz, float* __restrict__ entropy,
+                                float* __restrict__ logprob) {
   for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < n_rows;
        r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float m = -INFINITY;
-    for (int w = 0; w < world; ++w) m = fmaxf(m, stats_all[w * n_rows + r].x);
+    for (int w = 0; w < world; ++w) m = fmaxf(m, stats_all[w * world_stride4 + r].x);
     float s = 0.f, t = 0.f, xl = 0.f;
     for (int w = 0; w < world; ++w) {
-      const float4 st = stats_all[w * n_rows + r];
+      const float4 st = stats_all[w * world_stride4 + r];
       xl += st.w;
       const float f = st.x == -INFINITY ? 0.f : expf(st.x - m);
       s = fmaf(st.y, f, s);
@@ -173,7 +183,7 @@ __global__ void finalize_kernel(const float4* __restrict__ stats_all, int world,
     const float lz = m + logf(s);
     logz[r] = lz;
     entropy[r] = lz - t / s;
-    if (x_label_sum) x_label_sum[r] = xl;
+    if (logprob) logprob[r] = xl - lz;
   }
 }
 
@@ -187,6 +197,7 @@ __global__ void __launch_bounds__(kRowThreads) logprob_bwd_kernel(const T* __res
                                                                  const float* __restrict__ entropy,
                                                                  const float* __restrict__ g_entropy,
                                                                  const float* __restrict__ g_lp_rowsum,
+                                                                 const int64_t* __restrict__ labels, int64_t vocab_start,
                                                                  T* __restrict__ dlogits, int64_t d_row_stride) {
   constexpr int V = Vec<T>::N;
   constexpr int U = 4;
@@ -199,6 +210,9 @@ __global__ void __launch_bounds__(kRowThreads) logprob_bwd_kernel(const T* __res
     // d = inv_temp * p * (a * (-H - lp) - G),  lp = x - lz,  p = e^lp
     const float k0 = -(a * entropy[row] + G);
     const float c = inv_temp * kLog2e, lz2 = lz * kLog2e;
+    // one label per row: the one-hot term  + inv_temp * g_lp[row]  lands in the same pass (G is that row's g_lp)
+    const int64_t lc = labels != nullptr ? labels[row] - vocab_start : -1;
+    const float hot = inv_temp * G;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(q)) & 15) == 0;
     const int64_t n_vec = vec_ok ? n_cols / V : 0;
     for (int64_t v0 = static_cast<int64_t>(threadIdx.x) * U; v0 < n_vec; v0 += static_cast<int64_t>(kRowThreads) * U) {
@@ -215,6 +229,11 @@ __global__ void __launch_bounds__(kRowThreads) logprob_bwd_kernel(const T* __res
             const float pr = ex2(lp2);
             x[u * V + i] = inv_temp * pr * fmaf(-a * kLn2, lp2, k0);
           }
+          if (static_cast<uint64_t>(lc - (v0 + u) * V) < static_cast<uint64_t>(V)) {
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+              if ((v0 + u) * V + i == lc) x[u * V + i] += hot;
+          }
           Vec<T>::store(q + (v0 + u) * V, x + u * V);
         }
       }
@@ -222,7 +241,7 @@ __global__ void __launch_bounds__(kRowThreads) logprob_bwd_kernel(const T* __res
     for (int64_t i = n_vec * V + threadIdx.x; i < n_cols; i += kRowThreads) {
       const float lp2 = fmaf(Vec<T>::get(p + i), c, -lz2);
       const float pr = ex2(lp2);
-      Vec<T>::put(q + i, inv_temp * pr * fmaf(-a * kLn2, lp2, k0));
+      Vec<T>::put(q + i, inv_temp * pr * fmaf(-a * kLn2, lp2, k0) + (i == lc ? hot : 0.f));
     }
   }
 }
@@ -268,7 +287,8 @@ using namespace dta;
 extern "C" {
 
 int dta_logprob_row_stats(const void* logits, int dtype, int64_t n_rows, int64_t n_cols, int64_t row_stride,
-                          float inv_temperature, float* stats, dta_stream_t stream) {
+                          float inv_temperature, const int64_t* labels, int64_t vocab_start, float* stats,
+                          dta_stream_t stream) {
   DTA_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
   DTA_REQUIRE(n_rows >= 0 && n_cols >= 1 && row_stride >= n_cols, "bad logits shape");
   DTA_REQUIRE(inv_temperature > 0.f, "temperature must be positive");
@@ -277,10 +297,11 @@ int dta_logprob_row_stats(const void* logits, int dtype, int64_t n_rows, int64_t
   DTA_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 15) == 0, "stats must be 16-byte aligned");
   if (dtype == 0)
     row_stats_kernel<__nv_bfloat16><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(logits), n_rows, n_cols, row_stride, inv_temperature, stats);
+        static_cast<const __nv_bfloat16*>(logits), n_rows, n_cols, row_stride, inv_temperature, labels, vocab_start,
+        stats);
   else
-    row_stats_kernel<float><<<row_grid(n_rows), kRowThreads, 0, stream>>>(static_cast<const float*>(logits), n_rows,
-                                                                         n_cols, row_stride, inv_temperature, stats);
+    row_stats_kernel<float><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
+        static_cast<const float*>(logits), n_rows, n_cols, row_stride, inv_temperature, labels, vocab_start, stats);
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
 }
@@ -304,32 +325,36 @@ int dta_logprob_gather_labels(const void* logits, int dtype, int64_t n_cols, int
   return DTA_OK;
 }
 
-int dta_logprob_finalize(const float* stats_all, int world, int64_t n_rows, float* logz, float* entropy,
-                         float* x_label_sum, dta_stream_t stream) {
+int dta_logprob_finalize(const float* stats_all, int world, int64_t world_stride, int64_t n_rows, float* logz,
+                         float* entropy, float* logprob, dta_stream_t stream) {
   DTA_REQUIRE(world >= 1, "world must be >= 1");
   if (n_rows == 0) return DTA_OK;
   DTA_REQUIRE(stats_all && logz && entropy, "NULL pointer argument");
+  DTA_REQUIRE(world_stride >= 4 * n_rows && world_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(stats_all) & 15) == 0,
+              "stats_all: 16-byte aligned blocks of at least 4 * n_rows floats, world_stride a multiple of 4");
   finalize_kernel<<<small_grid(n_rows, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(stats_all), world,
-                                                               n_rows, logz, entropy, x_label_sum);
+                                                               world_stride / 4, n_rows, logz, entropy, logprob);
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
 }
 
 int dta_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t n_cols, int64_t row_stride,
                     float inv_temperature, const float* logz, const float* entropy, const float* g_entropy,
-                    const float* g_lp_rowsum, void* dlogits, int64_t d_row_stride, dta_stream_t stream) {
+                    const float* g_lp_rowsum, const int64_t* labels, int64_t vocab_start, void* dlogits,
+                    int64_t d_row_stride, dta_stream_t stream) {
   DTA_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (bf16) or 1 (fp32)");
   DTA_REQUIRE(n_rows >= 0 && n_cols >= 1 && row_stride >= n_cols && d_row_stride >= n_cols, "bad logits shape");
   if (n_rows == 0) return DTA_OK;
   DTA_REQUIRE(logits && logz && entropy && dlogits, "NULL pointer argument");
+  DTA_REQUIRE(labels == nullptr || g_lp_rowsum != nullptr, "labels (one per row) need the per-row g_lp in g_lp_rowsum");
   if (dtype == 0)
     logprob_bwd_kernel<__nv_bfloat16><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(logits), n_rows, n_cols, row_stride, inv_temperature, logz, entropy,
-        g_entropy, g_lp_rowsum, static_cast<__nv_bfloat16*>(dlogits), d_row_stride);
+        g_entropy, g_lp_rowsum, labels, vocab_start, static_cast<__nv_bfloat16*>(dlogits), d_row_stride);
   else
     logprob_bwd_kernel<float><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
         static_cast<const float*>(logits), n_rows, n_cols, row_stride, inv_temperature, logz, entropy, g_entropy,
-        g_lp_rowsum, static_cast<float*>(dlogits), d_row_stride);
+        g_lp_rowsum, labels, vocab_start, static_cast<float*>(dlogits), d_row_stride);
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
 }

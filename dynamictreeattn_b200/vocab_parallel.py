@@ -21,6 +21,7 @@ The same kernels serve the tree engine, where one logits row can carry several l
 """
 from __future__ import annotations
 
+from contextlib import nullcontext as _nullcontext
 from typing import Optional, Tuple
 
 import torch
@@ -49,10 +50,82 @@ def _tp_info(tp_group) -> Tuple[int, int]:
     return 1, 0
 
 
-def _forward_stats(x: torch.Tensor, labels: torch.Tensor, row_of: Optional[torch.Tensor], inv_temp: float,
-                   tp_group) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Shared forward: returns (x_label[M], logz[R], entropy[R]) — global over the TP group."""
+# ---------------------------------------------------------------------------------------------------------
+# kernel wrappers: the ONLY functions of this module that touch the C-ABI.  Everything above them (sharding,
+# the collective, autograd) is plain host logic; the CPU test-suite swaps these six for torch restatements
+# (tests/fake_backend.py) to run that logic under gloo.
+# ---------------------------------------------------------------------------------------------------------
+def _k_row_stats(x: torch.Tensor, inv_temp: float, labels: Optional[torch.Tensor], vocab_start: int,
+                 stats: torch.Tensor) -> None:
+    """stats[R,4] <- {max, sum e^(x-max), sum x e^(x-max), x[label] (one label per row, 0 outside the shard)}."""
     lib = _cabi.load()
+    R, V = x.shape
+    _cabi.check(lib.dta_logprob_row_stats(x.data_ptr(), _DTYPE_CODE[x.dtype], R, V, x.stride(0), inv_temp,
+                                          labels.data_ptr() if labels is not None else None, vocab_start,
+                                          stats.data_ptr(), _cabi.stream_ptr(x.device)))
+
+
+def _k_gather_labels(x: torch.Tensor, inv_temp: float, labels: torch.Tensor, row_of: torch.Tensor, vocab_start: int,
+                     out: torch.Tensor) -> None:
+    """out[m] <- x[row_of[m]][labels[m] - vocab_start] for labels in the shard, else 0 (several labels per row)."""
+    lib = _cabi.load()
+    _cabi.check(lib.dta_logprob_gather_labels(x.data_ptr(), _DTYPE_CODE[x.dtype], x.shape[1], x.stride(0), inv_temp,
+                                              labels.data_ptr(), row_of.data_ptr(), labels.numel(), vocab_start,
+                                              out.data_ptr(), 1, _cabi.stream_ptr(x.device)))
+
+
+def _k_finalize(blocks: torch.Tensor, n_rows: int, want_lp: bool):
+    """blocks [world, >= 4 n_rows] fp32 (row statistics first) -> (logz, entropy, logprob or None), each [n_rows]."""
+    lib = _cabi.load()
+    dev = blocks.device
+    logz = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    entropy = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    lp = torch.empty(n_rows, dtype=torch.float32, device=dev) if want_lp else None
+    _cabi.check(lib.dta_logprob_finalize(blocks.data_ptr(), blocks.shape[0], blocks.stride(0), n_rows, logz.data_ptr(),
+                                         entropy.data_ptr(), lp.data_ptr() if want_lp else None,
+                                         _cabi.stream_ptr(dev)))
+    return logz, entropy, lp
+
+
+def _k_backward(x: torch.Tensor, inv_temp: float, logz: torch.Tensor, entropy: torch.Tensor,
+                g_ent: Optional[torch.Tensor], g_rowsum: Optional[torch.Tensor], row_labels: Optional[torch.Tensor],
+                vocab_start: int, out: torch.Tensor) -> None:
+    """out <- d loss / d logits; with ``row_labels`` (one per row) the one-hot term is added in the same pass."""
+    lib = _cabi.load()
+    R, V = x.shape
+    _cabi.check(lib.dta_logprob_bwd(x.data_ptr(), _DTYPE_CODE[x.dtype], R, V, x.stride(0), inv_temp, logz.data_ptr(),
+                                    entropy.data_ptr(), g_ent.data_ptr() if g_ent is not None else None,
+                                    g_rowsum.data_ptr() if g_rowsum is not None else None,
+                                    row_labels.data_ptr() if row_labels is not None else None, vocab_start,
+                                    out.data_ptr(), out.stride(0), _cabi.stream_ptr(x.device)))
+
+
+def _k_rowsum(g_lp: torch.Tensor, row_of: torch.Tensor, n_rows: int) -> torch.Tensor:
+    """rowsum[r] = sum of g_lp over the labels attached to row r."""
+    lib = _cabi.load()
+    out = torch.zeros(n_rows, dtype=torch.float32, device=g_lp.device)
+    _cabi.check(lib.dta_logprob_rowsum_grad(g_lp.data_ptr(), row_of.data_ptr(), g_lp.numel(), out.data_ptr(),
+                                            _cabi.stream_ptr(g_lp.device)))
+    return out
+
+
+def _k_scatter(out: torch.Tensor, inv_temp: float, labels: torch.Tensor, row_of: torch.Tensor, g_lp: torch.Tensor,
+               vocab_start: int) -> None:
+    """out[row_of[m]][labels[m] - vocab_start] += inv_temp * g_lp[m] for labels in the shard (several per row)."""
+    lib = _cabi.load()
+    _cabi.check(lib.dta_logprob_bwd_scatter(out.data_ptr(), _DTYPE_CODE[out.dtype], out.shape[1], out.stride(0),
+                                            inv_temp, labels.data_ptr(), row_of.data_ptr(), g_lp.data_ptr(),
+                                            g_lp.numel(), vocab_start, _cabi.stream_ptr(out.device)))
+
+
+def _forward_stats(x: torch.Tensor, labels: torch.Tensor, row_of: Optional[torch.Tensor], inv_temp: float,
+                   tp_group) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], torch.Tensor, torch.Tensor]:
+    """Shared forward -> (logprob[R] | None, x_label[M] | None, logz[R], entropy[R]), global over the TP group.
+
+    Each rank fills ONE block of fp32 words — 16 bytes of statistics per row (the label logit rides in the 4th
+    word), followed, for trie rows with several labels (``row_of``), by one word per label — and the group
+    exchanges exactly that block in ONE all-gather (reference: 3-4 all-reduces, vocab_parallel.py:134,142,156 /
+    264,273,291,298)."""
     _cabi.require_cuda(x, labels)
     if x.dtype not in _DTYPE_CODE:
         raise _cabi.DtaError(f"logits dtype {x.dtype} not supported (bf16 or fp32)")
@@ -60,74 +133,52 @@ def _forward_stats(x: torch.Tensor, labels: torch.Tensor, row_of: Optional[torch
     M = labels.numel()
     world, rank = _tp_info(tp_group)
     dev = x.device
-    st = _cabi.stream_ptr(dev)
-    code = _DTYPE_CODE[x.dtype]
     labels = labels.reshape(-1).to(torch.int64)
     one_per_row = row_of is None
     if one_per_row and M != R:
         raise _cabi.DtaError(f"labels ({M}) and logits rows ({R}) disagree")
-    with torch.cuda.device(dev):
-        stats = torch.empty((R, 4), dtype=torch.float32, device=dev)
-        _cabi.check(lib.dta_logprob_row_stats(x.data_ptr(), code, R, V, x.stride(0), inv_temp, stats.data_ptr(), st))
-        if one_per_row:
-            # pack x[label] into the spare 4th word: the whole exchange is 16 B per row per rank
-            _cabi.check(lib.dta_logprob_gather_labels(x.data_ptr(), code, V, x.stride(0), inv_temp,
-                                                      labels.data_ptr(), None, M, rank * V,
-                                                      stats.data_ptr() + 12, 4, st))
-            x_label = None
-        else:
-            x_label = torch.empty(M, dtype=torch.float32, device=dev)
-            _cabi.check(lib.dta_logprob_gather_labels(x.data_ptr(), code, V, x.stride(0), inv_temp,
-                                                      labels.data_ptr(), row_of.data_ptr(), M, rank * V,
-                                                      x_label.data_ptr(), 1, st))
+    n_extra = 0 if one_per_row else (M + 3) // 4 * 4          # blocks stay 16-byte aligned
+    with torch.cuda.device(dev) if dev.type == "cuda" else _nullcontext():
+        block = torch.empty(4 * R + n_extra, dtype=torch.float32, device=dev)
+        _k_row_stats(x, inv_temp, labels if one_per_row else None, rank * V, block[:4 * R].view(R, 4))
+        if not one_per_row:
+            if n_extra > M:
+                block[4 * R + M:].zero_()
+            _k_gather_labels(x, inv_temp, labels, row_of, rank * V, block[4 * R:4 * R + M])
         if world > 1:
-            stats_all = torch.empty((world, R, 4), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(stats_all, stats, group=tp_group)
-            if x_label is not None:
-                dist.all_reduce(x_label, op=dist.ReduceOp.SUM, group=tp_group)
+            blocks = torch.empty((world, block.numel()), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(blocks.view(-1), block, group=tp_group)   # flat output: gloo and NCCL both take it
         else:
-            stats_all = stats
-        logz = torch.empty(R, dtype=torch.float32, device=dev)
-        entropy = torch.empty(R, dtype=torch.float32, device=dev)
-        xsum = torch.empty(R, dtype=torch.float32, device=dev) if one_per_row else None
-        _cabi.check(lib.dta_logprob_finalize(stats_all.data_ptr(), world, R, logz.data_ptr(), entropy.data_ptr(),
-                                             xsum.data_ptr() if one_per_row else None, st))
-    return (xsum if one_per_row else x_label), logz, entropy
+            blocks = block.view(1, -1)
+        logz, entropy, lp = _k_finalize(blocks, R, one_per_row)
+        x_label = None
+        if not one_per_row:
+            x_label = blocks[:, 4 * R:4 * R + M].sum(0) if world > 1 else block[4 * R:4 * R + M]
+    return lp, x_label, logz, entropy
 
 
 def _backward_logits(x: torch.Tensor, labels: torch.Tensor, row_of: Optional[torch.Tensor], inv_temp: float,
                      vocab_start: int, logz: torch.Tensor, entropy: torch.Tensor, g_lp: Optional[torch.Tensor],
                      g_ent: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """d loss / d logits for this shard; ``out`` may alias ``x`` (in place)."""
-    lib = _cabi.load()
+    """d loss / d logits for this shard (collective-free, like the reference's backward, vocab_parallel.py:324-370);
+    ``out`` may alias ``x`` (in place)."""
     R, V = x.shape
     dev = x.device
-    st = _cabi.stream_ptr(dev)
-    code = _DTYPE_CODE[x.dtype]
     labels = labels.reshape(-1).to(torch.int64)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev) if dev.type == "cuda" else _nullcontext():
         if out is None:
             out = torch.empty_like(x)
-        rowsum = None
         if g_lp is not None:
             g_lp = g_lp.reshape(-1).to(torch.float32).contiguous()
-            if row_of is None:
-                rowsum = g_lp
-            else:
-                rowsum = torch.zeros(R, dtype=torch.float32, device=dev)
-                _cabi.check(lib.dta_logprob_rowsum_grad(g_lp.data_ptr(), row_of.data_ptr(), g_lp.numel(),
-                                                        rowsum.data_ptr(), st))
         if g_ent is not None:
             g_ent = g_ent.reshape(-1).to(torch.float32).contiguous()
-        _cabi.check(lib.dta_logprob_bwd(x.data_ptr(), code, R, V, x.stride(0), inv_temp, logz.data_ptr(),
-                                        entropy.data_ptr(), g_ent.data_ptr() if g_ent is not None else None,
-                                        rowsum.data_ptr() if rowsum is not None else None, out.data_ptr(),
-                                        out.stride(0), st))
-        if g_lp is not None:
-            _cabi.check(lib.dta_logprob_bwd_scatter(out.data_ptr(), code, V, out.stride(0), inv_temp,
-                                                    labels.data_ptr(),
-                                                    row_of.data_ptr() if row_of is not None else None,
-                                                    g_lp.data_ptr(), g_lp.numel(), vocab_start, st))
+        if row_of is None:        # one label per row: a single launch
+            _k_backward(x, inv_temp, logz, entropy, g_ent, g_lp, labels if g_lp is not None else None, vocab_start, out)
+        else:
+            rowsum = _k_rowsum(g_lp, row_of, R) if g_lp is not None else None
+            _k_backward(x, inv_temp, logz, entropy, g_ent, rowsum, None, vocab_start, out)
+            if g_lp is not None:
+                _k_scatter(out, inv_temp, labels, row_of, g_lp, vocab_start)
     return out
 
 
@@ -135,14 +186,14 @@ class _LogProbEntropy(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits: torch.Tensor, labels: torch.Tensor, inv_temp: float, tp_group, want_entropy: bool):
         x = _as_rows(logits)
-        x_label, logz, entropy = _forward_stats(x, labels, None, inv_temp, tp_group)
+        lp, _, logz, entropy = _forward_stats(x, labels, None, inv_temp, tp_group)
         world, rank = _tp_info(tp_group)
         ctx.save_for_backward(x, labels, logz, entropy)
         ctx.inv_temp = inv_temp
         ctx.vocab_start = rank * x.shape[1]
         ctx.in_shape = logits.shape
         ctx.want_entropy = want_entropy
-        lp = (x_label - logz).reshape(labels.shape)
+        lp = lp.reshape(labels.shape)
         if want_entropy:
             return lp, entropy.reshape(labels.shape)
         return lp
@@ -187,7 +238,8 @@ def gather_logprobs_entropy(logits: torch.Tensor, labels: torch.Tensor, temperat
 def logprob_entropy_rows(x: torch.Tensor, labels: torch.Tensor, row_of: torch.Tensor, inv_temp: float = 1.0,
                          tp_group=None):
     """(x_label[M], logz[R], entropy[R]) for logits rows ``x`` [R, V]; no autograd."""
-    return _forward_stats(x, labels, row_of, inv_temp, tp_group)
+    _, x_label, logz, entropy = _forward_stats(x, labels, row_of, inv_temp, tp_group)
+    return x_label, logz, entropy
 
 
 logprob_entropy_rows_backward = _backward_logits

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTA_ABI_VERSION 2
+#define DTA_ABI_VERSION 3
 #define DTA_TILE 128 /* attention tile edge (queries and keys) */
 
 typedef struct CUstream_st* dta_stream_t;
@@ -139,32 +139,41 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
  * 324-370).  x = logit * inv_temperature.  dtype: 0 = bf16, 1 = fp32.
  * ------------------------------------------------------------------------------------- */
 
-/* One pass over logits[n_rows, n_cols] (row_stride elements): stats[r] = {m, sum e^(x-m),
- * sum x e^(x-m), 0} for this shard.  These 16 bytes per row are what ranks exchange. */
+/* One pass over logits[n_rows, n_cols] (row_stride elements): stats[r] = {m, sum e^(x-m), sum x e^(x-m), x_label}
+ * for this shard, x_label = x[r][labels[r] - vocab_start] if labels != NULL and the label falls in this shard,
+ * else 0 (the reference's masked label gather, vocab_parallel.py:145-156, in the same launch).  These 16 bytes per
+ * row are ALL a vocab-parallel rank exchanges. */
 int dta_logprob_row_stats(const void* logits, int dtype, int64_t n_rows, int64_t n_cols, int64_t row_stride,
-                          float inv_temperature, float* stats, dta_stream_t stream);
+                          float inv_temperature, const int64_t* labels, int64_t vocab_start, float* stats,
+                          dta_stream_t stream);
 
 /* x_label[m * x_stride] = x[row_of[m]][labels[m] - vocab_start] if the label falls in this shard
  * else 0.  row_of == NULL means row_of[m] = m.  row_of[m] < 0 yields 0 (root nodes have no
- * edge).  With one label per row, x_label = stats + 3 and x_stride = 4 packs the value into the
- * spare word of the row statistics, so a vocab-parallel rank exchanges 16 bytes per row in all. */
+ * edge).  For SEVERAL labels per row (trie edges: a fork row has one label per child); with one label per row
+ * dta_logprob_row_stats gathers it itself. */
 int dta_logprob_gather_labels(const void* logits, int dtype, int64_t n_cols, int64_t row_stride,
                               float inv_temperature, const int64_t* labels, const int32_t* row_of,
                               int64_t n_labels, int64_t vocab_start, float* x_label, int64_t x_stride,
                               dta_stream_t stream);
 
-/* Merge `world` shard statistics (stats_all[world, n_rows, 4]) with the online-softmax rule:
- * logz[r] = log sum_v e^x, entropy[r] = logz - E_p[x]; if x_label_sum != NULL it receives the sum
- * over shards of the 4th statistics word (the label logit packed by dta_logprob_gather_labels). */
-int dta_logprob_finalize(const float* stats_all, int world, int64_t n_rows, float* logz, float* entropy,
-                         float* x_label_sum, dta_stream_t stream);
+/* Merge `world` shard statistics with the online-softmax rule (the reference's MAX + 3 SUM all-reduces,
+ * vocab_parallel.py:262-304, after ONE all-gather): rank w's rows are stats_all[w * world_stride + 4 r .. + 4)
+ * (world_stride in floats, >= 4 n_rows; the gathered block may carry extra words behind the row statistics).
+ * logz[r] = log sum_v e^x, entropy[r] = logz - E_p[x]; logprob (may be NULL) = sum over shards of the 4th
+ * statistics word - logz = the log-prob of the row's label. */
+int dta_logprob_finalize(const float* stats_all, int world, int64_t world_stride, int64_t n_rows, float* logz,
+                         float* entropy, float* logprob, dta_stream_t stream);
 
 /* dlogits[r,c] = inv_temperature * p * ( g_entropy[r] * (-entropy[r] - log p) - g_lp_rowsum[r] ),
  * p = e^(x - logz[r]); written in `dtype`; dlogits may alias logits (in place).
- * g_lp_rowsum[r] = sum of g_lp over the labels attached to row r.  Either grad may be NULL. */
+ * g_lp_rowsum[r] = sum of g_lp over the labels attached to row r.  Either grad may be NULL.
+ * labels != NULL (ONE label per row; g_lp_rowsum[r] is then that label's g_lp): the one-hot term
+ * dlogits[r][labels[r] - vocab_start] += inv_temperature * g_lp_rowsum[r] is added in the same pass for labels in
+ * this shard (reference vocab_parallel.py:337-368), and no dta_logprob_bwd_scatter call is needed. */
 int dta_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t n_cols, int64_t row_stride,
                     float inv_temperature, const float* logz, const float* entropy, const float* g_entropy,
-                    const float* g_lp_rowsum, void* dlogits, int64_t d_row_stride, dta_stream_t stream);
+                    const float* g_lp_rowsum, const int64_t* labels, int64_t vocab_start, void* dlogits,
+                    int64_t d_row_stride, dta_stream_t stream);
 
 /* dlogits[row_of[m]][labels[m]-vocab_start] += inv_temperature * g_lp[m] for labels in the shard.
  * (row, label) pairs must be unique — true for trie edges and for one label per row. */

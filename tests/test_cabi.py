@@ -35,7 +35,7 @@ def test_argument_validation_without_gpu():
     rc = lib.dta_trie_linearize(None, None, 0, 0, 0, None, None, None, None, None, None, None)
     assert rc != 0
     assert b"n_leaf" in lib.dta_last_error()
-    rc = lib.dta_logprob_row_stats(None, 7, 1, 1, 1, 1.0, None, None)
+    rc = lib.dta_logprob_row_stats(None, 7, 1, 1, 1, 1.0, None, 0, None, None)
     assert rc != 0 and b"dtype" in lib.dta_last_error()
 
 

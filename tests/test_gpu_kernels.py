@@ -162,13 +162,18 @@ def test_vocab_shard_merge_equals_unsharded(world):
     stats_all = torch.empty((world, R, 4), dtype=torch.float32, device="cuda")
     for r in range(world):
         shard = logits[:, r * Vs:(r + 1) * Vs].contiguous()
-        _cabi.check(lib.dta_logprob_row_stats(shard.data_ptr(), 0, R, Vs, Vs, 1.0, stats_all[r].data_ptr(), st))
-        _cabi.check(lib.dta_logprob_gather_labels(shard.data_ptr(), 0, Vs, Vs, 1.0, labels.data_ptr(), None, R, r * Vs,
-                                                  stats_all[r].data_ptr() + 12, 4, st))
-    lz, ent, xl = (torch.empty(R, device="cuda") for _ in range(3))
-    _cabi.check(lib.dta_logprob_finalize(stats_all.data_ptr(), world, R, lz.data_ptr(), ent.data_ptr(), xl.data_ptr(), st))
+        # one launch per shard: row statistics + the masked label gather into the 4th word
+        _cabi.check(lib.dta_logprob_row_stats(shard.data_ptr(), 0, R, Vs, Vs, 1.0, labels.data_ptr(), r * Vs,
+                                              stats_all[r].data_ptr(), st))
+    own = torch.div(labels, Vs, rounding_mode="floor")
+    for r in range(world):                      # exactly the owning shard carries the label logit
+        assert bool((stats_all[r, :, 3][own != r] == 0).all())
+        assert torch.equal(stats_all[r, :, 3][own == r], logits[own == r, labels[own == r]].float())
+    lz, ent, lp = (torch.empty(R, device="cuda") for _ in range(3))
+    _cabi.check(lib.dta_logprob_finalize(stats_all.data_ptr(), world, 4 * R, R, lz.data_ptr(), ent.data_ptr(),
+                                         lp.data_ptr(), st))
     lpr, entr = tree_oracle.logprob_entropy(logits, labels)
-    assert ((xl - lz) - lpr).abs().max().item() < 1e-5
+    assert (lp - lpr).abs().max().item() < 1e-5
     assert (ent - entr).abs().max().item() < 5e-5
 
 

@@ -21,26 +21,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 import torch  # noqa: E402
 
 
-def trunk_fan(n_total: int, trunk: int, fan: int, vocab: int = 50000, seed: int = 0):
-    """Family A: shared trunk of `trunk` tokens, then `fan` equal leaves."""
-    g = torch.Generator().manual_seed(seed)
-    t = torch.randint(0, vocab, (trunk,), generator=g)
-    leaf = (n_total - trunk) // fan
-    firsts = torch.randperm(vocab, generator=g)[:fan]
-    out = []
-    for c in range(fan):
-        s = torch.randint(0, vocab, (leaf,), generator=g)
-        s[0] = firsts[c]
-        out.append(torch.cat([t, s]))
-    return out
-
-
-def bary(n_total: int, fan: int, levels: int, vocab: int = 50000, seed: int = 0):
-    """Family B: fan-out `fan` at each of `levels` levels, equal segments."""
-    n_seg = sum(fan ** l for l in range(levels + 1))
-    seg = max(n_total // n_seg, 1)
-    from trie_cases import synth_trie
-    return synth_trie(seed, seg, tuple([fan] * levels), (seg, seg), vocab=vocab, max_depth=1 << 30)
+from dynamictreeattn_b200.workloads import bary, synth_trie, trunk_fan  # noqa: E402,F401
 
 
 def run_case(name, seqs, iters, Hq=16, Hkv=8, permute="backward"):
@@ -89,7 +70,6 @@ def main():
     ap.add_argument("--n", type=int, default=16384)
     args = ap.parse_args()
     if args.case == "tau2":
-        from trie_cases import synth_trie
         run_case("tau2", synth_trie(0, 6144, (4, 2, 2), (1024, 3072), vocab=151936, max_depth=16384), args.iters)
     elif args.case == "chain":
         run_case(f"chain{args.n}", trunk_fan(args.n, 0, 1), args.iters)

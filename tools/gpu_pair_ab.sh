@@ -20,4 +20,4 @@ PAIR_SWEEP_COMMIT=$COMMIT timeout 150 python tools/bwd_pair_check.py --sweep tau
 timeout 60 python tools/bwd_pair_trace.py > $O/bwd_pair_trace.log 2>&1; head -2 $O/bwd_pair_trace.log; grep period $O/bwd_pair_trace.log
 DTA_BWD_PAIR=1 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_pair_on.log 2>&1; echo "pytest (pair on) exit $?"; tail -2 $O/pytest_gpu_pair_on.log
 python bench.py --no-cpu-baseline > $O/bench_n1_pair_off.json 2> $O/bench_n1_pair_off.err; echo "bench (pair off) exit $?"; cut -c1-160 $O/bench_n1_pair_off.json
-DTA_BWD_PAIR=auto python bench.py --no-cpu-baseline > $O/bench_n1_pair_auto.json 2> $O/bench_n1_pair_auto.err; echo "bench (pair auto) exit $?"; cut -c1-160 $O/bench_n1_pair_auto.json
+DTA_BWD_PAIR=auto python bench.py --no-cpu-baseline --no-dense-baseline > $O/bench_n1_pair_auto.json 2> $O/bench_n1_pair_auto.err; echo "bench (pair auto) exit $?"; cut -c1-160 $O/bench_n1_pair_auto.json
