@@ -122,11 +122,23 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
+    in_tree = "DTA_LIB_PATH" not in os.environ
+    may_build = build_if_missing and os.environ.get("DTA_NO_BUILD") != "1"
     if not _LIB_PATH.exists():
-        if not build_if_missing or os.environ.get("DTA_NO_BUILD") == "1":
+        if not may_build or not in_tree:
             raise DtaError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
         from ._build import build_library
         build_library()
+    elif in_tree:
+        # a library built from OTHER sources than the ones in the tree must not load silently (same ABI number,
+        # different kernels): compare the build stamp with a fresh digest of csrc/ + the header + the flags
+        from ._build import LIBDIR, _digest, build_library
+        stamp = LIBDIR / "build.sha256"
+        if not stamp.exists() or stamp.read_text().strip() != _digest():
+            if not may_build:
+                raise DtaError(f"{_LIB_PATH} is stale (csrc/ or include/dta_b200.h changed since it was built): run "
+                               "`python -c 'import __graft_entry__ as g; g.build()'`")
+            build_library()
     lib = C.CDLL(str(_LIB_PATH))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch

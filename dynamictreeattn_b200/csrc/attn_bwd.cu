@@ -52,8 +52,6 @@ static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr bool kDefaultDqTma = true;
 static constexpr int kDefaultL2Ahead = 0;
 static constexpr int kDefaultRedGap = 0;             // see the drain warps
-static constexpr int kDefaultHeadMajor = 0;
-static constexpr int kDefaultSpinWaits = 0;
 static constexpr int kDefaultBwdPoly = 0;            // of every 8 exponentials, on the FMA pipes
 
 struct BwdSmem {
@@ -96,9 +94,6 @@ struct BwdParams {
   int l2_ahead;            // L2 prefetch distance of the Q / dO tiles, in steps (0 = off)
   int red_gap;             // dependent integer ops between two dQ reds of a drain warp (issue pacing)
   int debug_flags;         // timing ablations / trace modes (see the uses); 0 in production
-  int spin_waits;          // 1: the per-step hand-off waits poll (mbar_wait_spin) instead of parking the warp
-  int head_major;          // launch order: every work item of KV head 0, then head 1, ... (Q / dO / dQ of ONE head pair
-                           // in L2 at a time) instead of the 8 heads of a key tile side by side
   long long* trace;        // debug timeline (NULL in production): [step][16] clock64 stamps of CTA 0
 };
 
@@ -149,11 +144,6 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + BwdSmem::misc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // hand-offs on the step's dependency chain: poll without a suspend hint when p.spin_waits (A/B knob DTA_BWD_SPIN)
-  const bool spin = p.spin_waits != 0;
-  auto wait_hot = [&](uint64_t* bar, uint32_t parity) {
-    if (spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
-  };
 
   // kWorkList: the CTA's job comes from the device-built work list (chunks of split key tiles), else it is the whole
   // live range of key tile k_order[blockIdx / Hkv].  The second form needs no list kernel, no spare CTAs and no
@@ -162,10 +152,8 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   // dta_attn_shape_t::bwd_whole_tiles when the launch is provably balanced without splitting.
   int jt, q_first, n_qt;
   bool split = false;
-  const int n_items = gridDim.x / p.n_kv_heads;
-  const int item_idx = p.head_major ? blockIdx.x % n_items : blockIdx.x / p.n_kv_heads;
   if constexpr (kWorkList) {
-    const int widx = item_idx;
+    const int widx = blockIdx.x / p.n_kv_heads;
     if (widx >= *p.n_work) return;                        // the grid is sized for the worst-case number of chunks
     const int32_t* item = reinterpret_cast<const int32_t*>(p.work) + 4 * widx;
     jt = item[0];                                         // key tile
@@ -173,11 +161,11 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     n_qt = item[2];                                       // query tiles in the chunk
     split = item[3] != 0;                                 // other CTAs hold the rest of this key tile's range
   } else {
-    jt = p.k_order[item_idx];
+    jt = p.k_order[blockIdx.x / p.n_kv_heads];
     q_first = jt;
     n_qt = p.k_qlast[jt] - jt + 1;
   }
-  const int kvh = p.head_major ? blockIdx.x / n_items : blockIdx.x % p.n_kv_heads;
+  const int kvh = blockIdx.x % p.n_kv_heads;
   const int k0 = jt * kT;
   const int n_iter = n_qt * p.group;
   const int kmin_end = p.kmin_end[jt];
@@ -324,7 +312,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           const uint32_t nph = st + 1 == kQStages ? stph ^ 1u : stph;
           const uint32_t not_first = it > 0 ? 1u : 0u;
           // dV += P^T dO
-          wait_hot(bar_p_full, it & 1);
+          mbar_wait(bar_p_full, it & 1);
           if (lane == 0) DTA_TRACE(0);
           mbar_wait(bar_do_full, it & 1);          // dO(it) landed (warp B checked it for dP^T(it); this warp has not)
           tc_fence_after();
@@ -368,7 +356,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           const bool has_next = it + 1 < n_iter;
           const uint32_t not_first = it > 0 ? 1u : 0u;
           // dQ^T = K^T dS^T (first, so the drain overlaps dK), dK += dS^T Q
-          wait_hot(bar_ds_full, it & 1);
+          mbar_wait(bar_ds_full, it & 1);
           if (lane == 0) DTA_TRACE(2);
           tc_fence_after();
           if (elect_one()) {
@@ -386,7 +374,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           // dP^T of the next step needs R1 back from the drain warps
           if (has_next) {
             mbar_wait(bar_do_full, (it + 1) & 1);
-            wait_hot(bar_r1_free, it & 1);
+            mbar_wait(bar_r1_free, it & 1);
             if (lane == 0) DTA_TRACE(4);
             tc_fence_after();
             issue_dp();
@@ -416,7 +404,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int vis_lo = k_idx - qbase, vis_hi = k_end - qbase;      // visible columns of this row: [lo, hi)
 
       // ---- P^T = exp2(S^T * scale_log2 - lse * log2e), masked -------------------------
-      wait_hot(bar_st_full, it & 1);
+      mbar_wait(bar_st_full, it & 1);
       if (threadIdx.x == 0) DTA_TRACE(6);
       tc_fence_after();
       float pr[64];
@@ -459,7 +447,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (threadIdx.x == 0) DTA_TRACE(7);
 
       // ---- dS^T = (scale P^T) o dP'^T -> smem (bf16, 128B-swizzled) --------------------
-      wait_hot(bar_dp_full, it & 1);
+      mbar_wait(bar_dp_full, it & 1);
       if (threadIdx.x == 0) DTA_TRACE(8);
       tc_fence_after();
       uint32_t dsp[32];
@@ -556,7 +544,7 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     for (int it = 0; it < n_iter; ++it) {
       const int head = kvh * p.group + it / n_qt;
       const int q0 = (q_first + it % n_qt) * kT;
-      wait_hot(bar_dq_full, it & 1);
+      mbar_wait(bar_dq_full, it & 1);
       if (threadIdx.x == 256) DTA_TRACE(10);
       tc_fence_after();
       float acc[128];
@@ -985,10 +973,13 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   const int n_tiles_ = sh->n_pad / DTA_TILE;
   DTA_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, dq_bytes, stream));
   const int enable_split = getenv("DTA_BWD_SPLIT") ? atoi(getenv("DTA_BWD_SPLIT")) : 1;   // 0: never split (A/B knob)
-  // experimental CTA-pair main kernel (attn_bwd_pair.cu): "1" = always, "auto" = for launches the caller marked balanced
-  // (bwd_whole_tiles; the pair kernel has no split chunks and pairing wastes 22-33 % of the steps on bushy tries)
+  // CTA-pair main kernel (attn_bwd_pair.cu): the pair kernel has no split chunks and pairing wastes 22-33 % of the
+  // steps on bushy tries, hence only for launches with bwd_whole_tiles
+  // DEFAULT ("auto"): the CTA-pair kernel for launches the caller marked balanced, the single-CTA work-list kernel
+  // otherwise; DTA_BWD_PAIR=0 / 1 force one of them (A/B, tests).  In the bench step the pair kernel runs the
+  // tau2 launch at 915-925 TFLOP/s against 895-905 (same box: profiles/r02/visit5_*.log, visit1_*.log).
   const char* pair_env = getenv("DTA_BWD_PAIR");
-  const bool use_pair = pair_env && (strcmp(pair_env, "auto") == 0 ? sh->bwd_whole_tiles != 0 : atoi(pair_env) != 0);
+  const bool use_pair = (!pair_env || strcmp(pair_env, "auto") == 0) ? sh->bwd_whole_tiles != 0 : atoi(pair_env) != 0;
   if (sh->bwd_whole_tiles != 0 || !enable_split || use_pair) {
     DTA_CHECK_CUDA(cudaMemsetAsync(n_work, 0, 16, stream));                      // n_split = 0: nothing to zero or convert
   } else {
@@ -1047,8 +1038,6 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   p.l2_ahead = getenv("DTA_BWD_L2PF") ? atoi(getenv("DTA_BWD_L2PF")) : kDefaultL2Ahead;
   p.red_gap = getenv("DTA_BWD_REDGAP") ? atoi(getenv("DTA_BWD_REDGAP")) : kDefaultRedGap;
   p.debug_flags = getenv("DTA_DEBUG_FLAGS") ? atoi(getenv("DTA_DEBUG_FLAGS")) : 0;
-  p.spin_waits = getenv("DTA_BWD_SPIN") ? atoi(getenv("DTA_BWD_SPIN")) : kDefaultSpinWaits;
-  p.head_major = getenv("DTA_BWD_HEAD_MAJOR") ? atoi(getenv("DTA_BWD_HEAD_MAJOR")) : kDefaultHeadMajor;
   p.trace = g_bwd_trace;
 
   using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,

@@ -138,8 +138,11 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
 }
 // Same instruction used as a pure SIGNAL to the leader (mask 1) by a thread that has no MMA outstanding: the commit
 // path delivered the leader's barriers to the peer within ~20 cycles where a remote mbarrier.arrive took 370-930
-// (docs/next_kernels.md 1.2).  UNTESTED variant (DTA_PAIR_HANDOFF=commit): whether a thread of the NON-leader CTA may
-// issue it is what tools/pair_handoff_bench.cu mode 3 finds out first.
+// (docs/next_kernels.md 1.2).  A/B variant (DTA_PAIR_HANDOFF=commit), measured on the B200 in round 2: a NON-leader
+// thread may issue it (tools/pair_handoff_bench.cu mode 3: 427 cycles round trip, load-independent, against 715-2590
+// for the arrive), gradients identical to the arrive form on every parity case -- and the kernel is 3 % SLOWER with it
+// (tau2: 14.16 vs 13.70 ms, profiles/r02/bwd_pair_sweep.log): the commit orders behind the issuing thread's proxy
+// traffic.  Kept for the A/B and covered by tests/test_gpu_kernels.py::test_bwd_cta_pair_commit_handoff_variant; not the default.
 __device__ __forceinline__ void commit_signal_leader(uint64_t* bar) {
   const uint16_t mask = 1;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(

@@ -49,7 +49,7 @@ struct FwdSmem {
   static constexpr int v = k + kStages * kTileBytes;           // kStages tiles
   static constexpr int live = v + kStages * kTileBytes;        // int32[kMaxLive]
   static constexpr int bars = live + kMaxLive * 4;             // mbarriers
-  static constexpr int n_bars = 1 + 4 * kStages + 10;
+  static constexpr int n_bars = 1 + 4 * kStages + 6;
   static constexpr int misc = bars + n_bars * 8;               // tmem addr, n_live
   static constexpr int total = misc + 16;
 };
@@ -65,22 +65,13 @@ struct FwdParams {
   int n_q_heads, n_kv_heads, group, pairs_per_kv;
   int64_t o_row_stride, o_head_stride;
   float scale_log2;
-  int flags;               // kFwdHeadMajor | kFwdSplitP | kFwdSplitS (A/B knobs, DTA_FWD_FLAGS)
-  long long* trace;        // debug timeline (NULL in production): [step][16] clock64 stamps of CTA 0
 };
-static constexpr int kFwdHeadMajor = 1;   // launch order: all query tiles of one KV head before the next head (L2 reuse of K/V)
-static constexpr int kFwdSplitP = 2;      // P leaves in two 64-key halves: PV starts on the first while the second is computed
-static constexpr int kFwdSplitS = 4;      // QK^T as two N = 64 MMAs with their own commits: the softmax starts on the first half
-static constexpr int kFwdSpinWaits = 8;   // S-ready / P-ready hand-offs poll without a suspend hint
-static constexpr int kDefaultFwdFlags = kFwdHeadMajor;
-
-#define DTA_FTRACE(ev)                                                                        \
-  do {                                                                                        \
-    if (p.trace != nullptr && blockIdx.x == 0 && it < 48) p.trace[it * 16 + (ev)] = clock64(); \
-  } while (0)
 
 // kPolyOf8: how many of every 8 exponentials run on the FMA pipes (poly_exp2) instead of MUFU
-template <int kPolyOf8>
+// kHeadMajor: launch order.  false: the head pairs of a query tile side by side (all KV heads resident at once);
+//             true: every query tile of head pair 0, then pair 1, ... -- the CTAs resident at one time then share ONE
+//             KV head's K / V (34 MB at 67k tokens, against 275 MB for all eight: the L2 holds 126 MB).
+template <int kPolyOf8, bool kHeadMajor>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const FwdParams p) {
@@ -99,8 +90,6 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* bar_s_full = bar_v_empty + kStages;   // [2] per tile
   uint64_t* bar_p_full = bar_s_full + 2;          // [2]
   uint64_t* bar_o_final = bar_p_full + 2;         // [2]
-  uint64_t* bar_p_half = bar_o_final + 2;         // [2] first 64 keys of P written (kFwdSplitP)
-  uint64_t* bar_s_half = bar_p_half + 2;          // [2] first 64 keys of S ready (kFwdSplitS)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + FwdSmem::misc);
   int* s_nlive = reinterpret_cast<int*>(smem + FwdSmem::misc + 4);
 
@@ -108,11 +97,8 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   // ---- which work item -----------------------------------------------------------------
   const int n_pairs = p.n_kv_heads * p.pairs_per_kv;
-  const bool head_major = (p.flags & kFwdHeadMajor) != 0;
-  const int qtile = p.q_order[head_major ? blockIdx.x % p.n_tiles : blockIdx.x / n_pairs];
-  const int pair = head_major ? blockIdx.x / p.n_tiles : blockIdx.x % n_pairs;
-  const bool split_p = (p.flags & kFwdSplitP) != 0, split_s = (p.flags & kFwdSplitS) != 0;
-  const bool spin = (p.flags & kFwdSpinWaits) != 0;
+  const int qtile = p.q_order[kHeadMajor ? blockIdx.x % p.n_tiles : blockIdx.x / n_pairs];
+  const int pair = kHeadMajor ? blockIdx.x / p.n_tiles : blockIdx.x % n_pairs;
   const int kvh = pair / p.pairs_per_kv;
   const int head_a = kvh * p.group + 2 * (pair % p.pairs_per_kv);
   const bool valid_b = (2 * (pair % p.pairs_per_kv) + 1) < p.group;
@@ -153,10 +139,8 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       for (int t = 0; t < 2; ++t) {
         mbar_init(bar_s_full + t, 1);
-        mbar_init(bar_p_full + t, 4);       // one arrival per softmax warp
+        mbar_init(bar_p_full + t, 128);
         mbar_init(bar_o_final + t, 1);
-        mbar_init(bar_p_half + t, 4);
-        mbar_init(bar_s_half + t, 1);
       }
       fence_mbar_init();
     }
@@ -199,7 +183,6 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // on one elected lane, so descriptor arithmetic stays on the uniform datapath (see attn_bwd.cu).
     {
       constexpr uint32_t idesc_qk = make_idesc_bf16(kBM, kBN, false, false);
-      constexpr uint32_t idesc_qk64 = make_idesc_bf16(kBM, kBN / 2, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(kBM, kD, false, true);
       const int n_t = valid_b ? 2 : 1;
       const uint32_t kQ = sdesc_lo_kmajor(smem_u32(sQ)), kK = sdesc_lo_kmajor(smem_u32(sK));
@@ -208,36 +191,21 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       auto issue_qk = [&](int t, int st) {
         if (elect_one()) {
           const uint32_t a = kQ + t * kTileW, b = kK + st * kTileW, d = tmem + t * 128;
-          if (split_s) {
-            // keys 0-63 = rows 0-63 of both K half-tiles, keys 64-127 = rows 64-127 (8 KB further: same swizzle phase)
 #pragma unroll
-            for (int kk = 0; kk < kD / 16; ++kk) {
-              const uint32_t off = (kk >> 2) * (kHalfBytes >> 4) + (kk & 3) * 2;
-              umma_ss_lo(d, a + off, b + off, idesc_qk64, kk > 0 ? 1u : 0u);
-            }
-            umma_commit(bar_s_half + t);
-#pragma unroll
-            for (int kk = 0; kk < kD / 16; ++kk) {
-              const uint32_t off = (kk >> 2) * (kHalfBytes >> 4) + (kk & 3) * 2;
-              umma_ss_lo(d + 64, a + off, b + off + (8192 >> 4), idesc_qk64, kk > 0 ? 1u : 0u);
-            }
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < kD / 16; ++kk) {
-              const uint32_t off = (kk >> 2) * (kHalfBytes >> 4) + (kk & 3) * 2;
-              umma_ss_lo(d, a + off, b + off, idesc_qk, kk > 0 ? 1u : 0u);
-            }
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * (kHalfBytes >> 4) + (kk & 3) * 2;
+            umma_ss_lo(d, a + off, b + off, idesc_qk, kk > 0 ? 1u : 0u);
           }
           umma_commit(bar_s_full + t);
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int t, int st, bool first, int kk0, int kk1) {     // k-steps [kk0, kk1) of 16 keys each
+      auto issue_pv = [&](int t, int st, bool first) {
         if (elect_one()) {
           const uint32_t b = nV + st * kTileW, a = tmem + t * 128, d = tmem + 256 + t * 128;
           const uint32_t acc0 = first ? 0u : 1u;
 #pragma unroll
-          for (int kk = kk0; kk < kk1; ++kk) umma_ts_lo(d, a + kk * 8, b + kk * (2048 >> 4), idesc_pv, kk > 0 ? 1u : acc0);
+          for (int kk = 0; kk < kBN / 16; ++kk) umma_ts_lo(d, a + kk * 8, b + kk * (2048 >> 4), idesc_pv, kk > 0 ? 1u : acc0);
         }
         __syncwarp();
       };
@@ -256,23 +224,10 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_wait(bar_v_full + st, ph);
         if (has_next) mbar_wait(bar_k_full + nst, nph);
         for (int t = 0; t < n_t; ++t) {
-          if (split_p) {
-            mbar_wait(bar_p_half + t, it & 1);
-            tc_fence_after();
-            if (lane == 0) DTA_FTRACE(4 + 4 * t);
-            issue_pv(t, st, it == 0, 0, 4);
-            mbar_wait(bar_p_full + t, it & 1);
-            tc_fence_after();
-            if (lane == 0) DTA_FTRACE(5 + 4 * t);
-            issue_pv(t, st, it == 0, 4, 8);
-          } else {
-            if (spin) mbar_wait_spin(bar_p_full + t, it & 1); else mbar_wait(bar_p_full + t, it & 1);
-            tc_fence_after();
-            if (lane == 0) DTA_FTRACE(5 + 4 * t);
-            issue_pv(t, st, it == 0, 0, 8);
-          }
+          mbar_wait(bar_p_full + t, it & 1);
+          tc_fence_after();
+          issue_pv(t, st, it == 0);
           if (has_next) issue_qk(t, nst);
-          if (lane == 0) DTA_FTRACE(6 + 4 * t);
         }
         if (elect_one()) {
           umma_commit(bar_v_empty + st);
@@ -303,28 +258,12 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       for (int it = 0; it < n_live; ++it) {
         const int entry = sLive[it];
         const int k0 = (entry >> 1) * kBN;
+        mbar_wait(bar_s_full + t, it & 1);
+        tc_fence_after();
         float s[kBN];
-        if (split_s) {
-          mbar_wait(bar_s_half + t, it & 1);
-          tc_fence_after();
-          if (threadIdx.x == t * 128) DTA_FTRACE(t * 2);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) tmem_ld_x32(tS + c * 32, reinterpret_cast<uint32_t*>(s) + c * 32);
-          tmem_ld_wait();
-          mbar_wait(bar_s_full + t, it & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int c = 2; c < 4; ++c) tmem_ld_x32(tS + c * 32, reinterpret_cast<uint32_t*>(s) + c * 32);
-          tmem_ld_wait();
-        } else {
-          if (spin) mbar_wait_spin(bar_s_full + t, it & 1); else mbar_wait(bar_s_full + t, it & 1);
-          tc_fence_after();
-          if (threadIdx.x == t * 128) DTA_FTRACE(t * 2);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, reinterpret_cast<uint32_t*>(s) + c * 32);
-          tmem_ld_wait();
-        }
-        if (threadIdx.x == t * 128) DTA_FTRACE(t * 2 + 1);
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, reinterpret_cast<uint32_t*>(s) + c * 32);
+        tmem_ld_wait();
 
         if (entry & 1) {  // boundary tile: per-element ancestor test
           const int4* ends = reinterpret_cast<const int4*>(p.subtree_end + k0);
@@ -388,12 +327,6 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             pk[i] = pack_bf16x2(p0, p1);
           }
           tmem_st_x16(tS + c * 16, pk);
-          if (c == 1 && split_p) {      // keys 0-63 of P are in TMEM: the issuer may start PV on them
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_p_half + t);
-          }
         }
         {
           float la, lb;
@@ -402,10 +335,7 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         tmem_st_wait();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p_full + t);
-        if (threadIdx.x == t * 128) DTA_FTRACE(12 + t);
-        if (threadIdx.x == t * 128 + 96) DTA_FTRACE(14 + t);
+        mbar_arrive(bar_p_full + t);
       }
 
       // ---- epilogue: O / l -> bf16, LSE -----------------------------------------------
@@ -452,10 +382,6 @@ tree_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
 using namespace dta;
 
-static long long* g_fwd_trace = nullptr;
-/* debug only (not in the public header): device buffer of 48*16 int64 receiving the step timeline of CTA 0 */
-extern "C" int dta_debug_set_fwd_trace(long long* buf) { g_fwd_trace = buf; return 0; }
-
 extern "C" int dta_tree_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
                                  const dta_attn_meta_t* meta, const dta_attn_shape_t* sh, dta_stream_t stream) {
   DTA_REQUIRE(q && k && v && out && lse && meta && sh, "NULL pointer argument");
@@ -493,8 +419,6 @@ extern "C" int dta_tree_attn_fwd(const void* q, const void* k, const void* v, vo
   p.o_row_stride = sh->o_row_stride;
   p.o_head_stride = sh->o_head_stride;
   p.scale_log2 = sh->scale * kLog2e;
-  p.flags = getenv("DTA_FWD_FLAGS") ? atoi(getenv("DTA_FWD_FLAGS")) : kDefaultFwdFlags;
-  p.trace = g_fwd_trace;
 
   const int smem_bytes = FwdSmem::total + 1024;
   using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);
@@ -503,8 +427,14 @@ extern "C" int dta_tree_attn_fwd(const void* q, const void* k, const void* v, vo
     // share of the exponentials computed on the FMA pipes; DTA_FWD_POLY (0, 2, 4, 6 or 8 of every 8) is a tuning knob
     const char* e = getenv("DTA_FWD_POLY");
     const int poly = e ? atoi(e) : kDefaultFwdPoly;
-    kernel = poly <= 1 ? tree_attn_fwd_kernel<0> : poly <= 3 ? tree_attn_fwd_kernel<2>
-           : poly <= 5 ? tree_attn_fwd_kernel<4> : poly <= 7 ? tree_attn_fwd_kernel<6> : tree_attn_fwd_kernel<8>;
+    const char* hm = getenv("DTA_FWD_HEAD_MAJOR");          // A/B knob; default: head-major
+    const bool head_major = hm ? atoi(hm) != 0 : true;
+    if (head_major)
+      kernel = poly <= 1 ? tree_attn_fwd_kernel<0, true> : poly <= 3 ? tree_attn_fwd_kernel<2, true>
+             : poly <= 5 ? tree_attn_fwd_kernel<4, true> : poly <= 7 ? tree_attn_fwd_kernel<6, true> : tree_attn_fwd_kernel<8, true>;
+    else
+      kernel = poly <= 1 ? tree_attn_fwd_kernel<0, false> : poly <= 3 ? tree_attn_fwd_kernel<2, false>
+             : poly <= 5 ? tree_attn_fwd_kernel<4, false> : poly <= 7 ? tree_attn_fwd_kernel<6, false> : tree_attn_fwd_kernel<8, false>;
     DTA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
   const int grid = p.n_tiles * p.n_kv_heads * p.pairs_per_kv;

@@ -68,31 +68,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Latency-critical waits (a hand-off on the step's dependency chain): plain try_wait polling, no suspend-time
-// hint -- the hinted form above parks the warp and its wake-up showed up as hundreds of cycles per hop in the
-// kernels' timelines.  Same bounded-spin safety net.
-__device__ __forceinline__ bool mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_nohint(bar, parity)) {
-    if (++spins > DTA_MBAR_SPIN_LIMIT) {
-      printf("dta: mbarrier timeout (spin) block=%d thread=%d bar=%u parity=%u\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
-    }
-  }
-}
-
 // ----------------------------------------------------------------------------
 // proxies / fences
 // ----------------------------------------------------------------------------

@@ -25,7 +25,7 @@ from .trie import CompressedTrie, _get_stats, _get_subtrie
 
 __all__ = [
     "LB_by_n_tokens", "LB_by_TM", "LB_by_DFS_and_TM", "pred_time", "get_original_bins",
-    "try_devide", "partition", "allreduce_gradients", "dp_backward",
+    "try_devide", "partition", "allreduce_gradients", "dp_backward", "GradientReducer",
 ]
 
 
@@ -161,13 +161,148 @@ def partition(token_seqs, K: int, method: str = "LB_by_DFS_and_TM", time_model=N
 # --------------------------------------------------------------------------
 # Part 2 — data-parallel runtime (new; one process per GPU, NCCL over NVLink)
 # --------------------------------------------------------------------------
-def allreduce_gradients(model: torch.nn.Module, group=None, bucket_bytes: int = 256 << 20) -> None:
-    """Sum ``param.grad`` over ranks with bucketed all-reduce.
+class GradientReducer:
+    """Sum this step's parameter gradients over ranks, overlapped with the backward pass.
 
-    NVSwitch gives every GPU full bandwidth to every peer, so buckets are sized
-    for launch latency (few, large) rather than link count.  Parameters whose
-    grad is None on this rank (empty bin) contribute zeros.
+    One preallocated flat buffer per gradient dtype holds the step's gradients; while a step is armed every
+    ``param.grad`` is a VIEW into it, so autograd accumulates in place and nothing is concatenated or copied back.
+    The buffer is cut into buckets in REVERSE parameter order (the order the backward produces gradients); a
+    post-accumulate-grad hook counts each parameter's arrivals and, when the last parameter of a bucket has
+    received the gradient of the step's last pass, starts that bucket's all-reduce asynchronously (NCCL's own
+    stream, ordered after the producing kernels) so that the exchange runs under the rest of the backward.  NVSwitch
+    gives every GPU full bandwidth to every peer: buckets are sized for launch latency and overlap, not link count.
+
+    The engine ACCUMULATES into ``param.grad`` and never zeroes it (reference tree_training_engine.py:487, 616), so
+    gradients a caller already holds are set aside during the step and the reduced step gradient is added to them
+    afterwards -- only the step's own contribution crosses the wire.
+
+    ``arm(n_passes)``: a trie over the memory budget runs as several sub-tries (TreeTrainingEngine._ranges), each
+    with its own backward; a bucket is reduced after the LAST of them.  ``finish()`` flushes what never fired
+    (parameters without a gradient on this rank: an empty bin contributes zeros) and waits for the exchange.
     """
+
+    def __init__(self, model: torch.nn.Module, group=None, bucket_bytes: int = 128 << 20):
+        self.group = group
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.flat = {}            # dtype -> flat buffer
+        self.slot = {}            # param -> (dtype, offset, numel)
+        self.buckets = []         # (dtype, lo, hi, [params])
+        self.bucket_of = {}
+        by_dtype = {}
+        for p in reversed(self.params):
+            by_dtype.setdefault(p.dtype, []).append(p)
+        for dtype, plist in by_dtype.items():
+            total = sum(p.numel() for p in plist)
+            self.flat[dtype] = torch.zeros(total, dtype=dtype, device=plist[0].device)
+            off, lo, members = 0, 0, []
+            esize = self.flat[dtype].element_size()
+            for p in plist:
+                self.slot[p] = (dtype, off, p.numel())
+                members.append(p)
+                off += p.numel()
+                if (off - lo) * esize >= bucket_bytes:
+                    self._close_bucket(dtype, lo, off, members)
+                    lo, members = off, []
+            if members:
+                self._close_bucket(dtype, lo, off, members)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._armed = False
+        self._kept = {}
+        self._arrivals = {}
+        self._pending = []
+        self._works = []
+        self._launched = set()
+        self.n_passes = 1
+        self.overlapped_buckets = 0     # buckets whose all-reduce started from a hook in the last step (diagnostic)
+
+    def _close_bucket(self, dtype, lo, hi, members):
+        idx = len(self.buckets)
+        self.buckets.append((dtype, lo, hi, list(members)))
+        for p in members:
+            self.bucket_of[p] = idx
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+    # ---- one step -----------------------------------------------------------------------------------------
+    def arm(self, n_passes: int = 1) -> None:
+        """Point every ``param.grad`` at its (zeroed) slot of the flat buffer; earlier gradients are kept aside."""
+        self.n_passes = max(1, int(n_passes))
+        self._kept = {}
+        for p in self.params:
+            dtype, off, n = self.slot[p]
+            if p.grad is not None:
+                mine = p.grad.data_ptr() == self.flat[dtype].data_ptr() + off * self.flat[dtype].element_size()
+                # a gradient still living in the flat buffer (last step's, never zeroed by the caller) moves out first
+                self._kept[p] = p.grad.clone() if mine else p.grad
+        for buf in self.flat.values():
+            buf.zero_()
+        for p in self.params:
+            dtype, off, n = self.slot[p]
+            p.grad = self.flat[dtype][off:off + n].view_as(p)
+        self._arrivals = {p: 0 for p in self.params}
+        self._pending = [len(b[3]) for b in self.buckets]
+        self._works, self._launched = [], set()
+        self.overlapped_buckets = 0
+        self._armed = True
+
+    def set_passes(self, n_passes: int) -> None:
+        """Called by the engine once it knows how many sub-tries (backward passes) this step runs as."""
+        self.n_passes = max(1, int(n_passes))
+
+    def _launch(self, idx: int) -> None:
+        dtype, lo, hi, _ = self.buckets[idx]
+        self._launched.add(idx)
+        self._works.append(dist.all_reduce(self.flat[dtype][lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                                           async_op=True))
+
+    def _on_grad(self, p: torch.Tensor) -> None:
+        if not self._armed:
+            return
+        self._arrivals[p] += 1
+        if self._arrivals[p] == self.n_passes:
+            idx = self.bucket_of[p]
+            self._pending[idx] -= 1
+            if self._pending[idx] == 0:
+                self._launch(idx)
+                self.overlapped_buckets += 1
+
+    def finish(self) -> None:
+        """Reduce what has not been reduced yet, wait, and hand the gradients back (added to any kept ones)."""
+        if not self._armed:
+            return
+        self._armed = False
+        for idx in range(len(self.buckets)):
+            if idx not in self._launched:
+                self._launch(idx)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        for p, old in self._kept.items():
+            old.add_(p.grad)
+            p.grad = old
+        self._kept = {}
+
+
+_REDUCERS = {}
+
+
+def _reducer_for(model, group) -> GradientReducer:
+    key = (id(model), id(group))
+    r = _REDUCERS.get(key)
+    if r is None or [id(p) for p in r.params] != [id(p) for p in model.parameters() if p.requires_grad]:
+        if r is not None:
+            r.close()
+        r = _REDUCERS[key] = GradientReducer(model, group)
+    return r
+
+
+def allreduce_gradients(model: torch.nn.Module, group=None, bucket_bytes: int = 256 << 20) -> None:
+    """Sum ``param.grad`` over ranks AFTER the backward (no overlap): bucketed all-reduce of whatever the gradients
+    hold.  Kept for callers that drive ``engine.backward`` themselves; ``dp_backward`` overlaps the exchange with
+    the backward through ``GradientReducer`` instead.  Parameters whose grad is None on this rank contribute zeros."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     params = [p for p in model.parameters() if p.requires_grad]
@@ -195,27 +330,43 @@ def allreduce_gradients(model: torch.nn.Module, group=None, bucket_bytes: int = 
 
 def dp_backward(engine, model, token_seqs, attachs, loss_fn: Callable, *, bins=None,
                 method: str = "LB_by_DFS_and_TM", time_model=None, block_size: Optional[int] = 2048,
-                group=None, permute: str = "ours") -> float:
+                group=None, permute: str = "ours", trie=None, layout=None, overlap: bool = True) -> float:
     """One data-parallel training step over a global batch of sequences.
 
-    Every rank computes the SAME partition (deterministic host code, no
-    broadcast needed), runs its bin through ``engine.backward`` and joins the
-    gradient all-reduce.  Returns the global loss (sum over ranks).
-    """
+    Every rank computes the SAME partition (deterministic host code, no broadcast needed), runs its bin through
+    ``engine.backward`` and the step's gradients are summed over ranks (``GradientReducer``: flat buffer,
+    reverse-order buckets, all-reduce overlapped with the backward).  Returns the global loss (sum over ranks).
+    ``trie`` / ``layout``: this rank's bin already built / already resident in HBM (skips the host trie build /
+    the H2D copy and linearisation: bench.py's device-resident timing)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    if bins is None:
-        bins = partition(token_seqs, world, method, time_model, "backward", block_size) if world > 1 \
-            else [list(range(len(token_seqs)))]
-    mine = bins[rank]
+    if trie is None and token_seqs is not None:
+        if bins is None:
+            bins = partition(token_seqs, world, method, time_model, "backward", block_size) if world > 1 \
+                else [list(range(len(token_seqs)))]
+        mine = bins[rank]
+        if mine:
+            trie = TokenTrie([token_seqs[i] for i in mine], [dict(attachs[i]) for i in mine])
+            if permute == "ours":
+                trie.backward_permute()
+    reducer = _reducer_for(model, group) if world > 1 and overlap else None
+    if reducer is not None:
+        reducer.arm(1)
+        engine.pass_count_listener = reducer.set_passes
     loss = 0.0
-    if mine:
-        trie = TokenTrie([token_seqs[i] for i in mine], [dict(attachs[i]) for i in mine])
-        if permute == "ours":
-            trie.backward_permute()
-        loss = engine.backward(model, trie, loss_fn, block_size=block_size)
-    allreduce_gradients(model, group)
+    try:
+        if trie is not None and trie.inputs:
+            if layout is not None:
+                loss = engine.backward_layout(model, trie, layout, loss_fn, block_size)
+            else:
+                loss = engine.backward(model, trie, loss_fn, block_size=block_size)
+    finally:
+        engine.pass_count_listener = None
+        if reducer is not None:
+            reducer.finish()
     if world > 1:
+        if reducer is None:
+            allreduce_gradients(model, group)
         t = torch.tensor([loss], dtype=torch.float64, device=next(model.parameters()).device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         loss = float(t.item())

@@ -96,7 +96,7 @@ class _EdgePlan:
     """Edges (parent row -> child node) grouped by parent row, so a chunk of logits rows
     maps to one contiguous run of labels."""
 
-    def __init__(self, layout: TrieLayout):
+    def __init__(self, layout: TrieLayout, chunk_rows: int):
         N = layout.n_nodes
         parent = layout.parent[:N]
         child = torch.nonzero(parent >= 0).squeeze(1)
@@ -106,11 +106,16 @@ class _EdgePlan:
         self.row = rows[order]                         # logits row the label is read from
         self.label = layout.tok[self.child]            # token of the child
         self.n_nodes = N
+        self.chunk_rows = chunk_rows
+        # edge range of every row chunk, ONE device read per step (not one per chunk and pass)
+        cuts = torch.arange(0, N + chunk_rows, chunk_rows, device=self.row.device).clamp_(max=N)
+        self.bounds = torch.searchsorted(self.row, cuts).tolist()
 
     def span(self, a: int, b: int) -> Tuple[int, int]:
-        bounds = torch.searchsorted(self.row, torch.tensor([a, b], device=self.row.device))
-        e0, e1 = bounds.tolist()
-        return e0, e1
+        """Edges whose label row lies in [a, b); (a, b) must be a chunk of the plan."""
+        i = a // self.chunk_rows
+        assert a == i * self.chunk_rows and b == min(a + self.chunk_rows, self.n_nodes)
+        return self.bounds[i], self.bounds[i + 1]
 
 
 class _TreeHeadLoss(torch.autograd.Function):
@@ -205,6 +210,7 @@ class TreeTrainingEngine:
         self.max_trie_tokens: Optional[int] = None    # None: derive from free HBM (CUDA) / unlimited (elsewhere)
         self.last_layout: Optional[TrieLayout] = None
         self.last_n_ranges = 1           # sub-tries the last forward/backward call ran as
+        self.pass_count_listener = None  # callable(n_passes): told how many backward passes a step runs as (DP reducer)
         self._budget_cache = {}
 
     # ---- memory-bounded execution ------------------------------------------------------------
@@ -296,7 +302,7 @@ class TreeTrainingEngine:
         (+ the logits chunks themselves when ``keep_logits``)."""
         N = layout.n_nodes
         dev = h.device
-        plan = _EdgePlan(layout)
+        plan = _EdgePlan(layout, chunk_rows)
         lp_nodes = torch.zeros(N, dtype=torch.float32, device=dev)
         ent_nodes = torch.empty(N, dtype=torch.float32, device=dev)
         logz = torch.empty(N, dtype=torch.float32, device=dev)
@@ -369,6 +375,8 @@ class TreeTrainingEngine:
         budget = self._token_budget(training=True)
         ranges = self._ranges(token_trie, budget) if budget is not None else None
         self.last_n_ranges = len(ranges) if ranges else 1
+        if self.pass_count_listener is not None:
+            self.pass_count_listener(self.last_n_ranges)
         if ranges:
             total = 0.0
             for sub in ranges:

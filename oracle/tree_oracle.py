@@ -7,6 +7,9 @@ fp32 CPU restatements of the floating-point side of the hot path:
   masked_tree_attention  softmax over ancestors, the definition the kernels implement
                          (HF models/qwen3/modeling_qwen3.py:252-291 attention with the mask of
                          SURVEY.md §9); eager, O(N^2), small inputs only
+  masked_tree_attention_grads
+                         the same definition with its gradients, evaluated block by block so that
+                         benchmark-size tries fit (used on the GPU box, fp32, no TF32)
   tree_stack_forward/backward
                          the reference's algorithm itself — DFS over the trie with a KV stack,
                          suffix-vs-prefix causal attention per push, gradients stitched through
@@ -93,6 +96,43 @@ def masked_tree_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sub
     p = torch.exp(s - lse[..., None])
     out = torch.einsum("hqk,hkd->hqd", p, vf).transpose(0, 1)
     return out, lse
+
+
+def masked_tree_attention_grads(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: torch.Tensor,
+                                subtree_end: torch.Tensor, scale: float, q_chunk: int = 2048):
+    """(out, dq, dk, dv) in fp32 of the SAME definition as ``masked_tree_attention``, evaluated one KV head and one
+    block of ``q_chunk`` queries at a time (autograd per block, gradients accumulated), so that benchmark-size tries
+    (16k-67k tokens, Hq 16 / Hkv 8) fit: a block materialises group x q_chunk x N fp32 scores instead of Hq x N x N.
+    Queries of block [a, b) can only see keys < b."""
+    N, Hq, D = q.shape
+    Hkv = k.shape[1]
+    g = Hq // Hkv
+    dev = q.device
+    end = subtree_end[:N].to(dev)
+    out = torch.empty((N, Hq, D), dtype=torch.float32, device=dev)
+    dq = torch.empty((N, Hq, D), dtype=torch.float32, device=dev)
+    dk = torch.zeros((N, Hkv, D), dtype=torch.float32, device=dev)
+    dv = torch.zeros((N, Hkv, D), dtype=torch.float32, device=dev)
+    for h in range(Hkv):
+        for a in range(0, N, q_chunk):
+            b = min(a + q_chunk, N)
+            qq = q[a:b, h * g:(h + 1) * g].float().transpose(0, 1).detach().requires_grad_(True)     # [g, nq, D]
+            kk = k[:b, h].float().detach().requires_grad_(True)                                       # [b, D]
+            vv = v[:b, h].float().detach().requires_grad_(True)
+            iq = torch.arange(a, b, device=dev)
+            ik = torch.arange(b, device=dev)
+            vis = (ik[None, :] <= iq[:, None]) & (iq[:, None] < end[None, :b])
+            sc = torch.einsum("gqd,kd->gqk", qq, kk) * scale
+            sc = sc.masked_fill(~vis[None], float("-inf"))
+            lse = torch.logsumexp(sc, dim=-1)
+            o = torch.einsum("gqk,kd->gqd", torch.exp(sc - lse[..., None]), vv)
+            o.backward(dout[a:b, h * g:(h + 1) * g].float().transpose(0, 1))
+            out[a:b, h * g:(h + 1) * g] = o.detach().transpose(0, 1)
+            dq[a:b, h * g:(h + 1) * g] = qq.grad.transpose(0, 1)
+            dk[:b, h] += kk.grad
+            dv[:b, h] += vv.grad
+            del sc, o, lse, vis
+    return out, dq, dk, dv
 
 
 # ----------------------------------------------------------------------------------------

@@ -79,3 +79,17 @@ def test_bench_dense_leg_records_failure_instead_of_raising():
     out = bench.dense_gpu_leg(model, seqs, [dict(bench.ATTACH) for _ in seqs], torch.device("cpu"))
     assert out["value"] is None and "error" in out and out["unit"] == "sequence tokens/s"
     assert all(p.grad is None for p in model.parameters())
+
+
+def test_stale_library_is_refused(monkeypatch):
+    """_cabi.load() compares lib/build.sha256 with a fresh digest of the sources: a library of the same ABI number
+    built from other sources raises instead of loading silently (when building is not allowed)."""
+    from dynamictreeattn_b200 import _build, _cabi
+    _cabi.load()                                        # make sure a current build exists
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_build, "_digest", lambda: "0" * 64)
+    with pytest.raises(_cabi.DtaError, match="stale"):
+        _cabi.load(build_if_missing=False)
+    monkeypatch.undo()
+    _cabi._lib = None
+    assert _cabi.load(build_if_missing=False) is not None

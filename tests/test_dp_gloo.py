@@ -83,3 +83,69 @@ def test_allreduce_handles_missing_grads_and_buckets(tmp_path):
     m = torch.nn.Linear(4, 3)
     allreduce_gradients(m)                     # not initialised: no-op, must not create grads
     assert m.weight.grad is None
+
+
+def _reducer_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, str(ROOT))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dynamictreeattn_b200.data_parallel import GradientReducer
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                torch.nn.Linear(16, 3), torch.nn.Linear(3, 2))
+    for p in model[5].parameters():            # a layer this step never touches: its gradient stays None -> zeros
+        pass
+    red = GradientReducer(model, bucket_bytes=300)          # tiny buckets: several per step
+    x = torch.randn(5, 6, generator=torch.Generator().manual_seed(10 + rank))
+    y = torch.randn(5, 6, generator=torch.Generator().manual_seed(20 + rank))
+    out = {}
+    # step 1: two backward passes (a trie cut into two ranges); nothing may be reduced after the first one
+    red.arm(2)
+    model[:5](x).square().sum().backward()
+    out["launched_after_pass1"] = len(red._launched)
+    model[:5](y).square().sum().backward()
+    out["overlapped"] = red.overlapped_buckets
+    red.finish()
+    out["step1"] = {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}
+    # step 2: gradients from step 1 are kept and the reduced step-2 gradient is ADDED (engine never zeroes)
+    red.arm(1)
+    model[:5](x + y).square().sum().backward()
+    red.finish()
+    out["step2"] = {n: p.grad.clone() for n, p in model.named_parameters()}
+    out["n_buckets"] = len(red.buckets)
+    torch.save(out, os.path.join(out_dir, f"red{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_gradient_reducer_semantics(tmp_path):
+    """Flat-buffer reducer: buckets fire from the hooks only after the LAST pass of a step, untouched parameters
+    contribute zeros, gradients held before a step survive it, and the result equals the sum over ranks."""
+    world = 2
+    mp.spawn(_reducer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(tmp_path / f"red{k}.pt", weights_only=False) for k in range(world)]
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                torch.nn.Linear(16, 3), torch.nn.Linear(3, 2))
+    xs = [torch.randn(5, 6, generator=torch.Generator().manual_seed(10 + k)) for k in range(world)]
+    ys = [torch.randn(5, 6, generator=torch.Generator().manual_seed(20 + k)) for k in range(world)]
+    for k in range(world):
+        model[:5](xs[k]).square().sum().backward()
+        model[:5](ys[k]).square().sum().backward()
+    want1 = {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}
+    for k in range(world):
+        model[:5](xs[k] + ys[k]).square().sum().backward()
+    want2 = {n: p.grad for n, p in model.named_parameters()}
+    assert r[0]["n_buckets"] >= 3
+    for k in range(world):
+        assert r[k]["launched_after_pass1"] == 0
+        assert r[k]["overlapped"] >= r[k]["n_buckets"] - 1      # all but the never-touched layer's bucket
+        for n in want1:
+            got = r[k]["step1"][n]
+            if want1[n] is None:
+                assert got is not None and float(got.abs().max()) == 0.0, n
+            else:
+                assert torch.allclose(got, want1[n], rtol=1e-5, atol=1e-6), n
+        for n in want2:
+            ref = want2[n] if want2[n] is not None else torch.zeros_like(r[k]["step2"][n])
+            assert torch.allclose(r[k]["step2"][n], ref, rtol=1e-5, atol=1e-6), n

@@ -181,3 +181,26 @@ def test_memory_bounded_ranges_give_the_same_result(cpu_backend):
     trie = TokenTrie(seqs, attachs(len(seqs)))
     assert abs(eng.backward(model, trie, loss_fn, block_size=None) - loss_whole) < 1e-4 * max(1.0, abs(loss_whole))
     assert eng.last_n_ranges >= 8
+
+
+def test_blockwise_attention_oracle_equals_definition():
+    """oracle.masked_tree_attention_grads (block-by-block evaluation used at benchmark sizes on the GPU box) is the
+    same function as the one-shot definition, including ragged last blocks and GQA."""
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    from dynamictreeattn_b200.workloads import synth_trie
+    from oracle import trie_oracle
+    trie = TokenTrie(synth_trie(1, 100, (3, 2), (40, 90), vocab=1000))
+    trie.backward_permute()
+    lin = trie_oracle.linearize([t.tolist() for t in trie.inputs], trie.lcp_lens)
+    N = len(lin["tok"])
+    se = torch.from_numpy(lin["subtree_end"])
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(N, 4, 16, generator=g).requires_grad_()
+    k = torch.randn(N, 2, 16, generator=g).requires_grad_()
+    v = torch.randn(N, 2, 16, generator=g).requires_grad_()
+    do = torch.randn(N, 4, 16, generator=g)
+    o, _ = tree_oracle.masked_tree_attention(q, k, v, se, 0.25)
+    o.backward(do)
+    o2, dq, dk, dv = tree_oracle.masked_tree_attention_grads(q.detach(), k.detach(), v.detach(), do, se, 0.25, q_chunk=97)
+    for a, b in ((o, o2), (q.grad, dq), (k.grad, dk), (v.grad, dv)):
+        assert (a.detach() - b).abs().max().item() < 2e-5

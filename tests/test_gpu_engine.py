@@ -146,3 +146,29 @@ def test_memory_bounded_ranges_on_device_and_default_budget():
     assert abs(loss1 - loss2) < 0.01 * abs(loss1)
     worst = max(((g2[n] - g1[n]).norm() / (g1[n].norm() + 1e-6)).item() for n in g1)
     assert worst < 6e-2, worst
+
+
+def test_qwen3_0p6b_28_layer_step_vs_fp32_cpu_oracle():
+    """The BENCHMARKED model depth: a full 28-layer Qwen3-0.6B-shaped step (hidden 1024, Hq 16 / Hkv 8, V 151,936,
+    seed-0 random init, bf16, every kernel of the product path) against the fp32 CPU oracle (the reference's
+    algorithm, oracle.tree_stack_backward) on the ~2.4k-token sample trie of the bench's CPU leg: loss and the
+    per-parameter |dg|/|g| of exp/compare_grads.py:42-59, bound by the reference's own bf16 artefact
+    (grad/Qwen3-0.6B-TB-vs-DB-bf16.txt:6,315: max 1.06e-1, median 2.55e-2).  The same function feeds bench.py's
+    `parity` object."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+    from dynamictreeattn_b200.tree_training_engine import TreeTrainingEngine
+    r = bench.cpu_reference_run(1, 0, keep_model=True)
+    cfg = bench.qwen3_config("0.6b")
+    torch.manual_seed(0)
+    model = Qwen3ForCausalLM(cfg).to("cuda", torch.bfloat16)          # same seed-0 weights as the CPU model
+    w_cpu = dict(r["model"].named_parameters())["model.layers.3.mlp.up_proj.weight"]
+    w_gpu = dict(model.named_parameters())["model.layers.3.mlp.up_proj.weight"]
+    assert torch.equal(w_cpu.detach().bfloat16(), w_gpu.detach().cpu())
+    eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 16384)
+    par = bench.full_model_parity(model, eng, r["model"], r["loss"], r["seqs"])
+    print("full-model parity:", {k: v for k, v in par.items() if k not in ("tolerance", "metric")})
+    assert par["n_params"] == 310                                      # 28 x 11 + 2, the 310 rows of the grad/ artefact
+    assert par["ok"], par

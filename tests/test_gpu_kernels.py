@@ -220,6 +220,42 @@ def test_tree_attention_fwd_bwd(name, heads, monkeypatch):
     assert _rel(q.grad, qr.grad) < 1e-2 and _rel(k.grad, kr.grad) < 1e-2 and _rel(v.grad, vr.grad) < 1e-2
 
 
+def _bench_shape(name):
+    from dynamictreeattn_b200.workloads import bary, tau2_trie, trunk_fan
+    return {"chain16k": lambda: trunk_fan(16384, 0, 1), "fan_p4096_b16": lambda: trunk_fan(16384, 4096, 16),
+            "bary_b64": lambda: bary(16384, 64, 1), "fan_p0_b64": lambda: trunk_fan(16384, 0, 64),
+            "tau2": lambda: tau2_trie(0)}[name]()
+
+
+@pytest.mark.parametrize("name", ["chain16k", "fan_p4096_b16", "bary_b64", "fan_p0_b64", "tau2"])
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_attention_parity_at_benchmarked_shapes(name, pair, monkeypatch):
+    """The shapes that are BENCHMARKED (BASELINE configs 2 and 5): 16k-token tries and the 67k-token tau2 trie at
+    Hq 16 / Hkv 8 / D 128, forward and backward, against the fp32 masked-attention definition evaluated block by
+    block on the same bf16 inputs (oracle/tree_oracle.masked_tree_attention_grads; no TF32).  Same tolerances as the
+    small cases: out rel-L2 <= 5e-3, dq/dk/dv <= 1e-2.  pair = "1": the CTA-pair backward kernel."""
+    from dynamictreeattn_b200.attention import tree_attention
+    from dynamictreeattn_b200.linearize import linearize_trie
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    if pair == "1" and name in ("bary_b64", "fan_p0_b64"):
+        pytest.skip("the pair kernel is never selected for bushy tries (no split chunks)")
+    monkeypatch.setenv("DTA_BWD_PAIR", pair)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    trie = TokenTrie(_bench_shape(name))
+    trie.backward_permute()
+    lay = linearize_trie(trie, "cuda")
+    q, k, v, do = _qkv(lay.n_nodes, 16, 8)
+    q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+    out = tree_attention(q, k, v, lay, 128 ** -0.5)
+    out.backward(do)
+    ref, dq, dk, dv = tree_oracle.masked_tree_attention_grads(q.detach(), k.detach(), v.detach(), do,
+                                                              lay.subtree_end[:lay.n_nodes].long(), 128 ** -0.5)
+    errs = {"out": _rel(out, ref), "dq": _rel(q.grad, dq), "dk": _rel(k.grad, dk), "dv": _rel(v.grad, dv)}
+    print(f"parity {name} pair={pair}: " + " ".join(f"{a}={b:.2e}" for a, b in errs.items()))
+    assert torch.isfinite(out.float()).all() and torch.isfinite(q.grad.float()).all()
+    assert errs["out"] < 5e-3 and errs["dq"] < 1e-2 and errs["dk"] < 1e-2 and errs["dv"] < 1e-2, errs
+
+
 def test_tree_attention_strided_views_and_lse():
     """q/k/v as HF hands them over: transposed views of one fused projection buffer."""
     from dynamictreeattn_b200.attention import TreeAttnFunction
@@ -366,7 +402,7 @@ def test_backward_schedules_agree_on_bushy_16k_trie(monkeypatch):
                                         ("deep_forks", (3, 3)), ("many_leaves", (4, 1)), ("forest", (4, 2)),
                                         ("adversarial", (2, 1)), ("tau2_mini", (4, 2))])
 def test_bwd_cta_pair_kernel_parity(name, heads, monkeypatch):
-    """The experimental CTA-pair backward main kernel (cta_group::2, DTA_BWD_PAIR=1, csrc/attn_bwd_pair.cu; odd and
+    """The CTA-pair backward main kernel (cta_group::2, csrc/attn_bwd_pair.cu: the default for balanced launches; odd and
     even key-tile counts, GQA groups 1-4) against the fp32 eager masked oracle at the same tolerances as the default
     kernel, and against the default kernel's own gradients."""
     from dynamictreeattn_b200.attention import tree_attention
@@ -387,6 +423,25 @@ def test_bwd_cta_pair_kernel_parity(name, heads, monkeypatch):
         assert torch.isfinite(got.float()).all() and _rel(got, want) < 1e-2
     for a, b in zip(grads["0"], grads["1"]):
         assert _rel(b, a) < 3e-3
+
+
+@pytest.mark.parametrize("name", ["chain_300", "deep_forks", "tau2_mini"])
+def test_bwd_cta_pair_commit_handoff_variant(name, monkeypatch):
+    """The pair kernel's alternative hand-off (DTA_PAIR_HANDOFF=commit: tcgen05.commit multicast as the signal to the
+    leader instead of a remote mbarrier.arrive; measured 3 % slower, kept as an A/B knob) gives the gradients of the
+    default form."""
+    from dynamictreeattn_b200.attention import tree_attention
+    trie, lay = _layout(name)
+    q, k, v, do = _qkv(lay.n_nodes, 4, 2)
+    monkeypatch.setenv("DTA_BWD_PAIR", "1")
+    grads = {}
+    for mode in ("arrive", "commit"):
+        monkeypatch.setenv("DTA_PAIR_HANDOFF", mode)
+        qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+        tree_attention(qq, kk, vv, lay, 128 ** -0.5).backward(do)
+        grads[mode] = (qq.grad, kk.grad, vv.grad)
+    for a, b in zip(grads["arrive"], grads["commit"]):
+        assert torch.isfinite(b.float()).all() and _rel(b, a) < 1e-4
 
 
 def test_constant_values_property_full_size():
