@@ -67,26 +67,53 @@ def _kernel_ready(t: torch.Tensor) -> torch.Tensor:
     return t if ok else t.contiguous()
 
 
+def tree_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, layout: TrieLayout, scale: float):
+    """Kernel call, no autograd: (q, k, v as handed to the kernel, out [N,Hq,D] bf16, lse [Hq,n_pad] fp32 base 2)."""
+    lib = _cabi.load()
+    _cabi.require_cuda(q, k, v)
+    if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
+        raise _cabi.DtaError("tree attention kernels take bf16 q/k/v")
+    if q.shape[0] != layout.n_nodes:
+        raise _cabi.DtaError(f"q has {q.shape[0]} rows but the trie has {layout.n_nodes} nodes")
+    q, k, v = _kernel_ready(q), _kernel_ready(k), _kernel_ready(v)
+    out = torch.empty((q.shape[0], q.shape[1], q.shape[2]), dtype=q.dtype, device=q.device)
+    lse = torch.empty((q.shape[1], layout.n_pad), dtype=torch.float32, device=q.device)
+    shape = _shape(layout, q, k, v, out, scale)
+    meta = layout.meta()
+    _arm_profile(lib, "fwd")
+    _cabi.check(lib.dta_tree_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                      lse.data_ptr(), C.byref(meta), C.byref(shape),
+                                      _cabi.stream_ptr(q.device)))
+    return q, k, v, out, lse
+
+
+def tree_attention_backward(q, k, v, out, lse, dout, layout: TrieLayout, scale: float):
+    """Kernel call, no autograd: (dq, dk, dv) bf16 with the shapes of q, k, v."""
+    lib = _cabi.load()
+    dout = dout.contiguous()
+    dq = torch.empty((q.shape[0], q.shape[1], q.shape[2]), dtype=q.dtype, device=q.device)
+    dk = torch.empty((k.shape[0], k.shape[1], k.shape[2]), dtype=k.dtype, device=k.device)
+    dv = torch.empty_like(dk)
+    # the kernel addresses dq/dk/dv with the q/k/v strides: give it same-stride views
+    shape = _shape(layout, dq, dk, dv, out, scale)
+    if (q.stride() != dq.stride()) or (k.stride() != dk.stride()) or (v.stride() != dv.stride()):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    ws = torch.empty(lib.dta_tree_attn_bwd_workspace_bytes(C.byref(shape)), dtype=torch.uint8, device=q.device)
+    meta = layout.meta()
+    _arm_profile(lib, "bwd")
+    _cabi.check(lib.dta_tree_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                      dout.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                      dv.data_ptr(), C.byref(meta), C.byref(shape), ws.data_ptr(),
+                                      _cabi.stream_ptr(q.device)))
+    return dq, dk, dv
+
+
 class TreeAttnFunction(torch.autograd.Function):
     """out[N,Hq,D] = softmax_over_ancestors(q k^T * scale) v   (bf16, fp32 accumulate)."""
 
     @staticmethod
     def forward(ctx, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, layout: TrieLayout, scale: float):
-        lib = _cabi.load()
-        _cabi.require_cuda(q, k, v)
-        if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
-            raise _cabi.DtaError("tree attention kernels take bf16 q/k/v")
-        if q.shape[0] != layout.n_nodes:
-            raise _cabi.DtaError(f"q has {q.shape[0]} rows but the trie has {layout.n_nodes} nodes")
-        q, k, v = _kernel_ready(q), _kernel_ready(k), _kernel_ready(v)
-        out = torch.empty((q.shape[0], q.shape[1], q.shape[2]), dtype=q.dtype, device=q.device)
-        lse = torch.empty((q.shape[1], layout.n_pad), dtype=torch.float32, device=q.device)
-        shape = _shape(layout, q, k, v, out, scale)
-        meta = layout.meta()
-        _arm_profile(lib, "fwd")
-        _cabi.check(lib.dta_tree_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
-                                          lse.data_ptr(), C.byref(meta), C.byref(shape),
-                                          _cabi.stream_ptr(q.device)))
+        q, k, v, out, lse = tree_attention_forward(q, k, v, layout, scale)
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.layout = layout
         ctx.scale = scale
@@ -94,25 +121,29 @@ class TreeAttnFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout: torch.Tensor):
-        lib = _cabi.load()
         q, k, v, out, lse = ctx.saved_tensors
-        layout: TrieLayout = ctx.layout
-        dout = dout.contiguous()
-        dq = torch.empty((q.shape[0], q.shape[1], q.shape[2]), dtype=q.dtype, device=q.device)
-        dk = torch.empty((k.shape[0], k.shape[1], k.shape[2]), dtype=k.dtype, device=k.device)
-        dv = torch.empty_like(dk)
-        # the kernel addresses dq/dk/dv with the q/k/v strides: give it same-stride views
-        shape = _shape(layout, dq, dk, dv, out, ctx.scale)
-        if (q.stride() != dq.stride()) or (k.stride() != dk.stride()) or (v.stride() != dv.stride()):
-            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-        ws = torch.empty(lib.dta_tree_attn_bwd_workspace_bytes(C.byref(shape)), dtype=torch.uint8, device=q.device)
-        meta = layout.meta()
-        _arm_profile(lib, "bwd")
-        _cabi.check(lib.dta_tree_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
-                                          dout.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
-                                          dv.data_ptr(), C.byref(meta), C.byref(shape), ws.data_ptr(),
-                                          _cabi.stream_ptr(q.device)))
+        dq, dk, dv = tree_attention_backward(q, k, v, out, lse, dout, ctx.layout, ctx.scale)
         return dq, dk, dv, None, None
+
+
+class TreeAttnFromSaved(torch.autograd.Function):
+    """The attention node of a RECOMPUTED layer (fused_layers._RecomputedLayer): the forward kernel already ran in
+    the first pass and its (out, lse) were kept, so the node hands `out` back without a launch; its backward is the
+    ordinary backward kernel on the recomputed (bit-identical) q, k, v."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, layout: TrieLayout, scale: float, out: torch.Tensor, lse: torch.Tensor):
+        q, k, v = _kernel_ready(q), _kernel_ready(k), _kernel_ready(v)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.layout = layout
+        ctx.scale = scale
+        return out.view(out.shape)
+
+    @staticmethod
+    def backward(ctx, dout: torch.Tensor):
+        q, k, v, out, lse = ctx.saved_tensors
+        dq, dk, dv = tree_attention_backward(q, k, v, out, lse, dout, ctx.layout, ctx.scale)
+        return dq, dk, dv, None, None, None, None
 
 
 def tree_attention(q, k, v, layout: TrieLayout, scale: Optional[float] = None) -> torch.Tensor:

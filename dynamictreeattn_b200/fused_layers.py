@@ -206,8 +206,76 @@ def supports_fused_trunk(model) -> bool:
     return p.is_cuda and p.dtype == torch.bfloat16
 
 
-def fused_trunk_forward(model, layout: TrieLayout) -> torch.Tensor:
-    """Last hidden state [N, hidden] (after the final norm) of the linearised trie."""
+def _layer_forward(layer, x, residual, n, hq, hkv, d, depth, table, eps, attn_fn):
+    """One decoder layer on the model's own parameters (HF models/qwen3/modeling_qwen3.py:252-291, 81-83);
+    ``attn_fn(q, k, v, scaling)`` is the attention node."""
+    at, mlp = layer.self_attn, layer.mlp
+    h, residual = add_rmsnorm(x, residual, layer.input_layernorm.weight, eps)
+    q, k, v = multi_linear(h, at.q_proj.weight, at.k_proj.weight, at.v_proj.weight)
+    q, k, v = q.view(n, hq, d), k.view(n, hkv, d), v.view(n, hkv, d)
+    q, k = qknorm_rope(q, k, at.q_norm.weight, at.k_norm.weight, depth, table, eps)
+    a = attn_fn(q, k, v, at.scaling)
+    o = F.linear(a.view(n, hq * d), at.o_proj.weight)
+    h, residual = add_rmsnorm(o, residual, layer.post_attention_layernorm.weight, eps)
+    gate, up = multi_linear(h, mlp.gate_proj.weight, mlp.up_proj.weight)
+    x = F.linear(swiglu(gate, up), mlp.down_proj.weight)
+    return x, residual
+
+
+class _RecomputedLayer(torch.autograd.Function):
+    """One decoder layer that keeps only its inputs (x, residual: 2 hidden-wide rows per token) and the attention
+    output + lse (the tensors the attention BACKWARD kernel needs and the only ones that are expensive to
+    reproduce), and recomputes everything else — norms, projections, RoPE, SwiGLU — when the gradient arrives.
+
+    This is the single-pass engine's counterpart of the reference's block-wise pop (tree_training_engine.py:489-513),
+    which bounds the live graph to one block: here the live graph is one LAYER of the whole trie.  The attention
+    forward kernel is NOT re-run (``TreeAttnFromSaved``); the recomputation costs the layer's forward GEMMs except
+    ``down_proj`` and the elementwise kernels, ~7 % of a step, against a 4-6x smaller activation footprint."""
+
+    @staticmethod
+    def forward(ctx, x, residual, layer, layout, n, hq, hkv, d, depth, table, eps):
+        from .attention import tree_attention_forward
+        kept = {}
+
+        def attn_first(q, k, v, scaling):
+            _, _, _, out, lse = tree_attention_forward(q, k, v, layout, scaling)
+            kept["out"], kept["lse"] = out, lse
+            return out
+
+        with torch.no_grad():
+            x_out, res_out = _layer_forward(layer, x, residual, n, hq, hkv, d, depth, table, eps, attn_first)
+        ctx.layer, ctx.layout, ctx.dims, ctx.eps = layer, layout, (n, hq, hkv, d), eps
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, residual if residual is not None else x.new_empty(0), kept["out"], kept["lse"], depth, table)
+        return x_out, res_out
+
+    @staticmethod
+    def backward(ctx, gx, gres):
+        from .attention import TreeAttnFromSaved
+        x, residual, out, lse, depth, table = ctx.saved_tensors
+        n, hq, hkv, d = ctx.dims
+        layout = ctx.layout
+        xd = x.detach().requires_grad_(True)
+        rd = residual.detach().requires_grad_(True) if ctx.has_res else None
+
+        def attn_again(q, k, v, scaling):
+            return TreeAttnFromSaved.apply(q, k, v, layout, scaling, out, lse)
+
+        with torch.enable_grad():
+            x_out, res_out = _layer_forward(ctx.layer, xd, rd, n, hq, hkv, d, depth, table, ctx.eps, attn_again)
+        outs, grads = [], []
+        for o, g in ((x_out, gx), (res_out, gres)):
+            if g is not None:
+                outs.append(o)
+                grads.append(g)
+        torch.autograd.backward(outs, grads)            # parameter gradients accumulate into param.grad directly
+        return (xd.grad, rd.grad if rd is not None else None) + (None,) * 9
+
+
+def fused_trunk_forward(model, layout: TrieLayout, recompute: bool = False) -> torch.Tensor:
+    """Last hidden state [N, hidden] (after the final norm) of the linearised trie.  ``recompute``: keep only each
+    layer's inputs and attention output and recompute the rest in the backward (``_RecomputedLayer``)."""
+    from .attention import tree_attention
     base = model.model
     cfg = model.config
     n = layout.n_nodes
@@ -217,16 +285,11 @@ def fused_trunk_forward(model, layout: TrieLayout) -> torch.Tensor:
     table = rope_table(base.rotary_emb, max(layout.lens) + 1, layout.tok.device)
     x = base.embed_tokens(layout.tok)                       # [N, hidden]
     residual = None
+    attn = lambda q, k, v, scaling: tree_attention(q, k, v, layout, scaling)      # noqa: E731
     for layer in base.layers:
-        at, mlp = layer.self_attn, layer.mlp
-        h, residual = add_rmsnorm(x, residual, layer.input_layernorm.weight, eps)
-        q, k, v = multi_linear(h, at.q_proj.weight, at.k_proj.weight, at.v_proj.weight)
-        q, k, v = q.view(n, hq, d), k.view(n, hkv, d), v.view(n, hkv, d)
-        q, k = qknorm_rope(q, k, at.q_norm.weight, at.k_norm.weight, depth, table, eps)
-        a = tree_attention(q, k, v, layout, at.scaling)
-        o = F.linear(a.view(n, hq * d), at.o_proj.weight)
-        h, residual = add_rmsnorm(o, residual, layer.post_attention_layernorm.weight, eps)
-        gate, up = multi_linear(h, mlp.gate_proj.weight, mlp.up_proj.weight)
-        x = F.linear(swiglu(gate, up), mlp.down_proj.weight)
+        if recompute and torch.is_grad_enabled():
+            x, residual = _RecomputedLayer.apply(x, residual, layer, layout, n, hq, hkv, d, depth, table, eps)
+        else:
+            x, residual = _layer_forward(layer, x, residual, n, hq, hkv, d, depth, table, eps, attn)
     h, _ = add_rmsnorm(x, residual, base.norm.weight, eps)
     return h

@@ -139,13 +139,55 @@ def test_memory_bounded_ranges_on_device_and_default_budget():
         return loss, {n: p.grad.float().clone() for n, p in model.named_parameters()}
 
     loss1, g1 = run()
-    assert eng.last_n_ranges == 1 and eng._token_budget(True) > 100_000
+    assert eng.last_n_ranges == 1 and eng._token_budget(True) > 100_000 and not eng.last_recompute
+    from transformers import Qwen3Config as _C
+    deep = TreeTrainingEngine(_C(vocab_size=151936, hidden_size=1024, intermediate_size=3072, num_hidden_layers=28,
+                                 num_attention_heads=16, num_key_value_heads=8, head_dim=128), "cuda", torch.bfloat16, 16384)
+    assert deep._token_budget(True, recompute=True) > 2 * deep._token_budget(True)      # 28 layers: recomputation pays
     eng.max_trie_tokens = 600
     loss2, g2 = run()
     assert eng.last_n_ranges >= 2
     assert abs(loss1 - loss2) < 0.01 * abs(loss1)
     worst = max(((g2[n] - g1[n]).norm() / (g1[n].norm() + 1e-6)).item() for n in g1)
     assert worst < 6e-2, worst
+
+
+def test_layer_recompute_same_gradients_less_memory():
+    """Per-layer activation recomputation (fused_layers._RecomputedLayer; the engine's answer to the reference's
+    block-wise pop, tree_training_engine.py:489-513): same loss, the same gradients up to bf16 accumulation order,
+    the attention FORWARD kernel is not launched a second time, and the peak of live memory drops."""
+    from dynamictreeattn_b200 import _cabi
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    from dynamictreeattn_b200.tree_training_engine import TreeTrainingEngine
+    cfg = Qwen3Config(vocab_size=2048, hidden_size=512, intermediate_size=1536, num_hidden_layers=6,
+                      num_attention_heads=4, num_key_value_heads=2, head_dim=128, max_position_embeddings=8192,
+                      tie_word_embeddings=True)
+    torch.manual_seed(0)
+    model = Qwen3ForCausalLM(cfg).to("cuda", torch.bfloat16)
+    seqs = synth_trie(15, 1500, (3, 2), (300, 900), vocab=2048)
+    attachs = [{"w_logprobs": -1.0, "w_entropy": 0.1} for _ in seqs]
+    eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 8192)
+    res = {}
+    for rec in (False, True):
+        eng.recompute = rec
+        model.zero_grad(set_to_none=True)
+        trie = TokenTrie(seqs, [dict(a) for a in attachs])
+        trie.backward_permute()
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        before = dict(_cabi.call_count)
+        loss = eng.backward(model, trie, tree_oracle.example_loss, block_size=2048)
+        torch.cuda.synchronize()
+        calls = {k: _cabi.call_count.get(k, 0) - before.get(k, 0) for k in ("dta_tree_attn_fwd", "dta_tree_attn_bwd")}
+        res[rec] = (loss, {n: p.grad.float().clone() for n, p in model.named_parameters()},
+                    torch.cuda.max_memory_allocated() - base, calls)
+        assert eng.last_recompute == rec and eng.last_n_ranges == 1
+    assert res[True][3] == res[False][3] == {"dta_tree_attn_fwd": 6, "dta_tree_attn_bwd": 6}
+    assert abs(res[True][0] - res[False][0]) < 1e-3 * abs(res[False][0])
+    worst = max(((res[True][1][n] - g).norm() / (g.norm() + 1e-6)).item() for n, g in res[False][1].items())
+    assert worst < 2e-2, worst
+    assert res[True][2] < 0.6 * res[False][2], (res[True][2], res[False][2])
 
 
 def test_qwen3_0p6b_28_layer_step_vs_fp32_cpu_oracle():
@@ -172,3 +214,41 @@ def test_qwen3_0p6b_28_layer_step_vs_fp32_cpu_oracle():
     print("full-model parity:", {k: v for k, v in par.items() if k not in ("tolerance", "metric")})
     assert par["n_params"] == 310                                      # 28 x 11 + 2, the 310 rows of the grad/ artefact
     assert par["ok"], par
+
+
+def test_qwen3_1p7b_tau2_trie_runs_in_one_pass_with_recompute():
+    """Qwen3-1.7B (hidden 2048, MLP 6144, 28 layers; the first model of the reference's sweeps, exp/exp_tree.py) on
+    the 67k-token tau2 trie: full activations (~2.2 MB per token) do not fit 180 GB, so the engine switches to
+    per-layer recomputation and still runs the trie in ONE pass (no DFS range splitting, no recomputed prefixes).
+    Forcing recomputation off makes it fall back to ranges; both give the same loss."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    from dynamictreeattn_b200.tree_training_engine import TreeTrainingEngine
+    from dynamictreeattn_b200.workloads import tau2_trie
+    cfg = bench.qwen3_config("1.7b")
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        model = Qwen3ForCausalLM(cfg).to(torch.bfloat16)
+    seqs = tau2_trie(0)
+    eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 16384)
+    out = {}
+    for rec in (None, False):
+        eng.recompute = rec
+        model.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        trie = TokenTrie(seqs, [dict(bench.ATTACH) for _ in seqs])
+        trie.backward_permute()
+        loss = eng.backward(model, trie, bench.example_loss, block_size=2048)
+        torch.cuda.synchronize()
+        g = model.model.layers[13].mlp.down_proj.weight.grad.float().clone()
+        out[rec] = (loss, eng.last_n_ranges, eng.last_recompute, torch.cuda.max_memory_allocated() / 2 ** 30, g)
+        assert torch.isfinite(g).all()
+    print("1.7B tau2:", {str(k): v[:4] for k, v in out.items()})
+    assert out[None][1] == 1 and out[None][2] is True                 # one pass, recomputed layers
+    assert out[False][1] >= 2 and out[False][2] is False              # ranges when recomputation is off
+    assert abs(out[None][0] - out[False][0]) < 2e-3 * abs(out[False][0])
+    assert ((out[None][4] - out[False][4]).norm() / out[False][4].norm()).item() < 5e-2
