@@ -23,6 +23,7 @@ INCLUDE = PKG.parent / "include"
 SOURCES = [
     "dta_common.cu",
     "trie_kernels.cu",
+    "trie_build.cu",
     "logprob_kernels.cu",
     "attn_fwd.cu",
     "attn_bwd.cu",

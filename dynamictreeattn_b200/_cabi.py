@@ -18,7 +18,7 @@ import torch
 _LIB_PATH = Path(os.environ.get("DTA_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libdta_b200.so")
 _lib = None
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 TILE = 128
 
 
@@ -55,6 +55,8 @@ SIGNATURES = {
     "dta_trie_linearize": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "dta_trie_paths": (_I, [_P, _P, _P, _I, _P, _L, _P, _P, _P]),
     "dta_tile_meta": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dta_trie_build_workspace_bytes": (_Z, [_I]),
+    "dta_trie_build": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "dta_tree_attn_fwd": (_I, [_P, _P, _P, _P, _P, C.POINTER(AttnMeta), C.POINTER(AttnShape), _P]),
     "dta_profile_next_attn": (_I, [_P, _P]),
     "dta_tree_attn_bwd_workspace_bytes": (_Z, [C.POINTER(AttnShape)]),
@@ -77,7 +79,7 @@ SIGNATURES = {
 
 # kernels launched per successful call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
-    "dta_lcp_adjacent": 1, "dta_trie_linearize": 2, "dta_trie_paths": 1, "dta_tile_meta": 2,
+    "dta_lcp_adjacent": 1, "dta_trie_linearize": 2, "dta_trie_paths": 1, "dta_tile_meta": 2, "dta_trie_build": 3,
     "dta_tree_attn_fwd": 1, "dta_tree_attn_bwd": 4,
     "dta_logprob_row_stats": 1, "dta_logprob_gather_labels": 1, "dta_logprob_finalize": 1,
     "dta_logprob_bwd": 1, "dta_logprob_bwd_scatter": 1, "dta_logprob_rowsum_grad": 1,

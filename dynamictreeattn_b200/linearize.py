@@ -109,18 +109,28 @@ def linearize(inputs: Sequence[torch.Tensor], lens: Sequence[int], lcp_lens: Seq
     total_path = sum(lens)
 
     # host staging: the new tokens of each leaf, back to back, plus the integer plan
-    tok_host = torch.cat([ids[s:].reshape(-1).to("cpu", torch.int64) for ids, s in zip(inputs, starts)])
-    assert tok_host.numel() == n_nodes
+    on_device = all(ids.is_cuda for ids in inputs)
+    if on_device:           # CUDA-resident rollouts: the new tokens of each leaf are gathered on the device
+        tok_host = None
+    else:
+        tok_host = torch.cat([ids[s:].reshape(-1).to("cpu", torch.int64) for ids, s in zip(inputs, starts)])
+        assert tok_host.numel() == n_nodes
     plan = torch.tensor(lens + lcp_lens, dtype=torch.int32)
     path_off = [0] * (n_leaf + 1)
     for i, l in enumerate(lens):
         path_off[i + 1] = path_off[i] + l
     poff_host = torch.tensor(path_off, dtype=torch.int64)
     if torch.cuda.is_available():
-        tok_host, plan, poff_host = tok_host.pin_memory(), plan.pin_memory(), poff_host.pin_memory()
+        plan, poff_host = plan.pin_memory(), poff_host.pin_memory()
+        if tok_host is not None:
+            tok_host = tok_host.pin_memory()
 
     with torch.cuda.device(device):
-        tok = tok_host.to(device, non_blocking=True)
+        if on_device:
+            tok = torch.cat([ids[s:].reshape(-1).to(device=device, dtype=torch.int64) for ids, s in zip(inputs, starts)])
+            assert tok.numel() == n_nodes
+        else:
+            tok = tok_host.to(device, non_blocking=True)
         plan_d = plan.to(device, non_blocking=True)
         poff_d = poff_host.to(device, non_blocking=True)
         lens_d, lcp_d = plan_d[:n_leaf], plan_d[n_leaf:]
@@ -175,3 +185,37 @@ def lcp_adjacent_device(inputs: Sequence[torch.Tensor]) -> Tuple[List[int], bool
                                          out[-1:].data_ptr(), _cabi.stream_ptr(dev)))
         host = out.cpu().tolist()
     return host[:n - 1], bool(host[-1])
+
+
+MAX_DEVICE_BUILD_SEQ = 2048          # DTA_TRIE_BUILD_MAX_SEQ: the all-pairs tables are n_seq^2
+
+
+def trie_build_device(inputs: Sequence[torch.Tensor], presorted: bool = False) -> dict:
+    """Stable sort + leafization + forward / backward leaf orders of CUDA-resident rollouts in three launches
+    (csrc/trie_build.cu), one D2H copy of the plan.  Returns Python lists:
+    ``perm`` (sorted position -> input index), ``absorbed``, ``leaf_pos``, ``leaf_lcp``, ``order_fwd`` / ``lcp_fwd``,
+    ``order_bwd`` / ``lcp_bwd`` and ``unsorted`` (adjacent input pairs out of order).  Bit-exact with the host code."""
+    lib = _cabi.load()
+    dev = inputs[0].device
+    n = len(inputs)
+    if n > MAX_DEVICE_BUILD_SEQ:
+        raise _cabi.DtaError(f"device trie build handles up to {MAX_DEVICE_BUILD_SEQ} sequences (got {n})")
+    lens = [int(t.numel()) for t in inputs]
+    off = [0] * (n + 1)
+    for i, l in enumerate(lens):
+        off[i + 1] = off[i] + l
+    with torch.cuda.device(dev):
+        tokens = torch.cat([t.reshape(-1).to(torch.int64) for t in inputs]) if off[-1] > 0 else \
+            torch.zeros(1, dtype=torch.int64, device=dev)
+        off_d = torch.tensor(off, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+        ws = torch.empty(lib.dta_trie_build_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        out = torch.empty(2 + 9 * n, dtype=torch.int32, device=dev)
+        _cabi.check(lib.dta_trie_build(tokens.data_ptr(), off_d.data_ptr(), n, 1 if presorted else 0, ws.data_ptr(),
+                                       out.data_ptr(), _cabi.stream_ptr(dev)))
+        host = out.cpu().tolist()
+    n_leaf, unsorted = host[0], host[1]
+    seg = lambda k, m: host[2 + k * n:2 + k * n + m]        # noqa: E731
+    return {"n_leaf": n_leaf, "unsorted": unsorted, "perm": seg(0, n), "slcp": seg(1, max(n - 1, 0)),
+            "absorbed": seg(2, n), "leaf_pos": seg(3, n_leaf), "leaf_lcp": seg(4, max(n_leaf - 1, 0)),
+            "order_fwd": seg(5, n_leaf), "lcp_fwd": seg(6, max(n_leaf - 1, 0)),
+            "order_bwd": seg(7, n_leaf), "lcp_bwd": seg(8, max(n_leaf - 1, 0)), "lens": lens}

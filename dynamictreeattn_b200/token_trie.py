@@ -12,7 +12,11 @@ reference; the implementation differs:
   pair, no device sync per pair (reference: one ``.item()`` each,
   token_trie.py:6-10).  When the sequences already live on a CUDA device the
   adjacent-LCP + sortedness check runs in one launch of the ``dta_lcp_adjacent``
-  kernel instead.
+  kernel instead;
+* rollouts that live on a CUDA device (the usual case in RL: they were just generated there) never come back to
+  the host token by token: sort, leafization and BOTH leaf orders are computed by ``dta_trie_build``
+  (csrc/trie_build.cu: all-pairs LCP + rank sort + one planning CTA) and one small plan is copied back
+  (SURVEY.md section 8f, N2).  ``forward_permute`` / ``backward_permute`` then apply the precomputed order.
 """
 from __future__ import annotations
 
@@ -108,6 +112,11 @@ class TokenTrie:
         for seq_id in range(len(inputs)):
             attachs[seq_id]["_sequence_batch_id"] = seq_id
 
+        self._device_plan = None
+        if self._use_device_build(inputs):
+            self._init_from_device(inputs, attachs, sorted)
+            return
+
         if not sorted:
             keys = _sort_keys([_as_np(t) for t in inputs])
             perm = list(range(len(inputs)))
@@ -123,6 +132,46 @@ class TokenTrie:
         self.n_sequences = len(inputs)
         self.n_tokens = sum(len(ids) for ids in inputs)
 
+    # ---- device-side build (CUDA-resident rollouts) -------------------------
+    @staticmethod
+    def _use_device_build(inputs) -> bool:
+        if len(inputs) < 2 or not all(torch.is_tensor(t) and t.is_cuda and t.dim() == 1 for t in inputs):
+            return False
+        from . import linearize
+        return len(inputs) <= linearize.MAX_DEVICE_BUILD_SEQ
+
+    def _init_from_device(self, inputs, attachs, presorted: bool) -> None:
+        from . import linearize
+        plan = linearize.trie_build_device(inputs, presorted)
+        if presorted and plan["unsorted"]:
+            raise ValueError("Input_ids not sorted in lexicographic order.")
+        perm, lens = plan["perm"], plan["lens"]
+        self.inputs, self.attach_lists = [], []
+        members = []
+        for r, src in enumerate(perm):                  # sorted order; a leaf closes the run of absorbed prefixes
+            members.append((attachs[src], lens[src]))
+            if not plan["absorbed"][r]:
+                self.inputs.append(inputs[src])
+                self.attach_lists.append(members)
+                members = []
+        self.lcp_lens = list(plan["leaf_lcp"])
+        self.lens = [len(ids) for ids in self.inputs]
+        self.n_sequences = len(inputs)
+        self.n_tokens = sum(lens)
+        self._device_plan = plan
+
+    def _apply_device_order(self, which: str) -> bool:
+        """Apply a leaf order the device build already computed (valid only for the leaf order it was computed for)."""
+        plan, self._device_plan = self._device_plan, None
+        if plan is None:
+            return False
+        order = plan["order_" + which]
+        self.inputs = [self.inputs[i] for i in order]
+        self.attach_lists = [self.attach_lists[i] for i in order]
+        self.lens = [self.lens[i] for i in order]
+        self.lcp_lens = list(plan["lcp_" + which])
+        return True
+
     # ---- stats -------------------------------------------------------------
     def get_stats(self, mode: str, block_size: Optional[int] = None) -> dict:
         stats = _get_stats(self.lens, self.lcp_lens, mode, block_size)
@@ -133,17 +182,24 @@ class TokenTrie:
     # ---- leaf reordering ---------------------------------------------------
     def permute(self, order: Sequence[int]) -> None:
         """Reorder leaves and recompute adjacent LCPs from the tokens (token_trie.py:90-94)."""
+        self._device_plan = None
         self.inputs = [self.inputs[i] for i in order]
         self.attach_lists = [self.attach_lists[i] for i in order]
         self.lens = [self.lens[i] for i in order]
-        self.lcp_lens = _adjacent_lcps([_as_np(t) for t in self.inputs], self.inputs,
-                                       check_sorted=False)
+        if self.inputs and self.inputs[0].is_cuda:
+            self.lcp_lens = _adjacent_lcps([], self.inputs, check_sorted=False)     # dta_lcp_adjacent, no host copy
+        else:
+            self.lcp_lens = _adjacent_lcps([_as_np(t) for t in self.inputs], self.inputs, check_sorted=False)
 
     def forward_permute(self) -> None:
+        if self._apply_device_order("fwd"):
+            return
         order, _, _ = CompressedTrie(self.lens, self.lcp_lens).get_order_forward()
         self.permute(order)
 
     def backward_permute(self) -> None:
+        if self._apply_device_order("bwd"):
+            return
         order, _, _ = CompressedTrie(self.lens, self.lcp_lens).get_order_backward()
         self.permute(order)
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTA_ABI_VERSION 3
+#define DTA_ABI_VERSION 4
 #define DTA_TILE 128 /* attention tile edge (queries and keys) */
 
 typedef struct CUstream_st* dta_stream_t;
@@ -65,6 +65,27 @@ int dta_trie_linearize(const int32_t* lens, const int32_t* lcp, int n_leaf, int 
 int dta_trie_paths(const int32_t* lens, const int32_t* lcp, const int32_t* leaf_off, int n_leaf,
                    const int64_t* path_off, int64_t total, int32_t* path, const void* workspace,
                    dta_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-side trie build for CUDA-resident rollouts: the STABLE lexicographic sort
+ * (reference token_trie.py:68-73), _leafization (token_trie.py:13-49) and the leaf orders of forward_permute /
+ * backward_permute (trie.py:190-202, 225-233) with the LCPs TokenTrie.permute recomputes (token_trie.py:94) —
+ * bit-exact with the reference's host code.  tokens: the sequences back to back (int64, signed compare);
+ * offsets[n_seq + 1]: exclusive scan of their lengths.  presorted != 0: keep the given order (TokenTrie(sorted=True)).
+ * out: int32[2 + 9 * n_seq], n = n_seq:
+ *   out[0] n_leaf          out[1] number of ADJACENT INPUT pairs that are out of order (sorted=True check)
+ *   +2      perm[n]        sorted position -> input index
+ *   +2+n    slcp[n]        LCP of sorted sequence r with r + 1 (last: 0)
+ *   +2+2n   absorbed[n]    1: sorted sequence r is a full prefix of its successor (folded into a later leaf)
+ *   +2+3n   leaf_pos[n]    leaf j -> its sorted position          +2+4n  leaf_lcp[n]  LCP of leaf j with leaf j + 1
+ *   +2+5n   order_fwd[n]   get_order_forward() over the leaves    +2+6n  lcp_fwd[n]   LCPs after forward_permute
+ *   +2+7n   order_bwd[n]   get_order_backward()                   +2+8n  lcp_bwd[n]   LCPs after backward_permute
+ * (leaf-indexed arrays hold n_leaf resp. n_leaf - 1 valid entries).  One small D2H copy of `out` gives the host
+ * everything it needs to size the linearisation. */
+#define DTA_TRIE_BUILD_MAX_SEQ 2048
+size_t dta_trie_build_workspace_bytes(int n_seq);
+int dta_trie_build(const int64_t* tokens, const int64_t* offsets, int n_seq, int presorted, void* workspace,
+                   int32_t* out, dta_stream_t stream);
 
 /* Per-tile mask summaries and work orders for the attention kernels (n_tiles = n_pad/DTA_TILE):
  *   kmax_end[t], kmin_end[t] : max / min of subtree_end over the VALID keys of tile t

@@ -79,6 +79,106 @@ def test_lcp_adjacent_bit_exact(name):
 
 
 # ------------------------------------------------------------------------------------------
+# device-side trie build (N2): stable sort, leafization, forward / backward leaf orders -- bit-exact
+# ------------------------------------------------------------------------------------------
+def _golden_cases():
+    import json
+    from pathlib import Path
+    return json.loads((Path(__file__).parent / "golden" / "trie_cases.json").read_text())
+
+
+def _same_trie(a, b):
+    assert [x.tolist() for x in a.inputs] == [x.tolist() for x in b.inputs]
+    assert a.lens == b.lens and a.lcp_lens == b.lcp_lens
+    ids = lambda t: [[(m["_sequence_batch_id"], l) for m, l in al] for al in t.attach_lists]     # noqa: E731
+    assert ids(a) == ids(b)
+    assert (a.n_sequences, a.n_tokens) == (b.n_sequences, b.n_tokens)
+
+
+def test_device_trie_build_matches_reference_golden_vectors():
+    """dta_trie_build on CUDA-resident sequences against the vectors the UNMODIFIED reference produced
+    (tests/golden/trie_cases.json: sorted leaves, lens, lcp_lens, attach lists, get_order_forward/backward, the trie
+    after backward_permute) -- stable tie-breaking on duplicates, full-prefix merging, forests."""
+    from dynamictreeattn_b200 import _cabi
+    from dynamictreeattn_b200.linearize import trie_build_device
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    n_dev = 0
+    for c in _golden_cases():
+        seqs = [torch.tensor(s, dtype=torch.long, device="cuda") for s in c["seqs"]]
+        before = _cabi.call_count.get("dta_trie_build", 0)
+        t = TokenTrie(seqs, [{} for _ in seqs])
+        used_device = _cabi.call_count.get("dta_trie_build", 0) > before
+        n_dev += used_device
+        assert used_device == (len(seqs) >= 2)
+        assert [x.tolist() for x in t.inputs] == c["inputs"]
+        assert t.lens == c["lens"] and t.lcp_lens == c["lcp_lens"]
+        assert [[[a["_sequence_batch_id"], l] for a, l in al] for al in t.attach_lists] == [list(map(list, al)) for al in c["attach"]]
+        assert (t.n_sequences, t.n_tokens) == (c["n_sequences"], c["n_tokens"])
+        if used_device:
+            plan = trie_build_device(seqs)
+            assert plan["order_fwd"] == c["order_forward"][0] and plan["order_bwd"] == c["order_backward"][0]
+            assert [t.lens[i] for i in plan["order_fwd"]] == c["order_forward"][1]
+            assert plan["lcp_fwd"] == c["order_forward"][2] and plan["lcp_bwd"] == c["order_backward"][2]
+        t.backward_permute()
+        assert t.lens == c["after_backward_permute"]["lens"] and t.lcp_lens == c["after_backward_permute"]["lcp_lens"]
+        assert [x[:4].tolist() for x in t.inputs] == c["after_backward_permute"]["inputs_head"]
+    assert n_dev >= 20
+
+
+@pytest.mark.parametrize("name", list(CASES) + ["random_40", "random_300", "dups", "tau2_x3", "negative_ids"])
+def test_device_trie_build_equals_host_build(name):
+    """CUDA-resident input (device build) vs the same sequences on the host (the reference-exact host code): the
+    tries, both permuted tries and the error contract are identical."""
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    from dynamictreeattn_b200.workloads import tau2_trie
+    if name in CASES:
+        seqs = CASES[name]
+    elif name == "random_40":
+        seqs = random_seqs(21, 40, vocab=3, max_len=30)
+    elif name == "random_300":
+        seqs = random_seqs(22, 300, vocab=6, max_len=60)
+    elif name == "dups":
+        base = random_seqs(23, 12, vocab=4, max_len=20)
+        seqs = base + [b.clone() for b in base] + [b[:max(1, len(b) // 2)].clone() for b in base]
+    elif name == "negative_ids":
+        seqs = [s - 2 for s in random_seqs(24, 30, vocab=5, max_len=16)]
+    else:
+        seqs = tau2_trie(0) + tau2_trie(1) + [s[:5000].clone() for s in tau2_trie(0)[:3]]
+    for mode in ("none", "forward", "backward"):
+        host = TokenTrie([s.clone() for s in seqs], [{} for _ in seqs])
+        dev = TokenTrie([s.cuda() for s in seqs], [{} for _ in seqs])
+        if mode != "none":
+            getattr(host, mode + "_permute")()
+            getattr(dev, mode + "_permute")()
+        _same_trie(host, dev)
+        # a second permutation goes through the generic path (device LCP kernel) and still agrees
+        host.forward_permute()
+        dev.forward_permute()
+        _same_trie(host, dev)
+    if len(seqs) > 1:
+        srt = sorted(seqs, key=lambda t: t.tolist())
+        _same_trie(TokenTrie([s.clone() for s in srt], sorted=True), TokenTrie([s.cuda() for s in srt], sorted=True))
+        if srt[0].tolist() != srt[-1].tolist():
+            with pytest.raises(ValueError, match="not sorted"):
+                TokenTrie([s.cuda() for s in srt[::-1]], sorted=True)
+
+
+def test_engine_accepts_cuda_resident_rollouts():
+    """The whole path with rollouts that never visit the host: device trie build -> device linearisation -> layout
+    identical to the host-input one."""
+    from dynamictreeattn_b200.linearize import linearize_trie
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    seqs = CASES["tau2_mini"]
+    a = TokenTrie(seqs)
+    a.backward_permute()
+    b = TokenTrie([s.cuda() for s in seqs])
+    b.backward_permute()
+    la, lb = linearize_trie(a, "cuda"), linearize_trie(b, "cuda")
+    for key in ("tok", "depth", "parent", "subtree_end", "leaf_of", "leaf_off", "path", "kmax_end", "k_order", "q_order"):
+        assert torch.equal(getattr(la, key), getattr(lb, key)), key
+
+
+# ------------------------------------------------------------------------------------------
 # logprob / entropy
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype,V,R", [(torch.float32, 1000, 37), (torch.float32, 151936, 9), (torch.bfloat16, 151936, 33),
