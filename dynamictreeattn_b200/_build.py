@@ -25,6 +25,7 @@ SOURCES = [
     "trie_kernels.cu",
     "trie_build.cu",
     "logprob_kernels.cu",
+    "head_fwd.cu",
     "attn_fwd.cu",
     "attn_bwd.cu",
     "attn_bwd_pair.cu",

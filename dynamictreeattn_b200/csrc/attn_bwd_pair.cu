@@ -216,7 +216,10 @@ __device__ __forceinline__ void pwait(uint64_t* bar, uint32_t parity) { pwait_im
 __device__ __forceinline__ void pwait_cluster(uint64_t* bar, uint32_t parity) { pwait_impl<true>(bar, parity); }
 
 // kPolyOf8: how many of every 8 exponentials of the P^T pass run on the FMA pipes (poly_exp2), as in attn_bwd.cu
-template <int kPolyOf8>
+// kHeadMajor: launch order -- every key-tile pair of KV head 0, then head 1, ... (Q / dO / dQ of one head pair in L2 at a
+// time) instead of the KV heads of a pair side by side; compile-time so that the step loop's code is the same
+static constexpr bool kDefaultPairHeadMajor = false;
+template <int kPolyOf8, bool kHeadMajor>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __grid_constant__ CUtensorMap tmap_q128,
                           const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -254,8 +257,9 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
   const bool leader = rank == 0;
 
   const int cid = blockIdx.x >> 1;                    // cluster index
-  const int pj = p.pair_order[cid / p.n_kv_heads];
-  const int kvh = cid % p.n_kv_heads;
+  const int n_pairs_all = (p.n_tiles + 1) >> 1;
+  const int pj = p.pair_order[kHeadMajor ? cid % n_pairs_all : cid / p.n_kv_heads];
+  const int kvh = kHeadMajor ? cid / n_pairs_all : cid % p.n_kv_heads;
   const int t0 = 2 * pj;
   const int jt = t0 + static_cast<int>(rank);         // this CTA's key tile (may be one past the last tile: all masked)
   int qlast = p.k_qlast[t0];
@@ -767,7 +771,9 @@ int launch(const void* q, const void* k, const void* v, const void* dout, const 
 
   using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                           const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
-  static const Kernel kernels[3] = {tree_attn_bwd_pair_kernel<0>, tree_attn_bwd_pair_kernel<2>, tree_attn_bwd_pair_kernel<4>};
+  static const Kernel kernels[6] = {tree_attn_bwd_pair_kernel<0, false>, tree_attn_bwd_pair_kernel<2, false>,
+                                    tree_attn_bwd_pair_kernel<4, false>, tree_attn_bwd_pair_kernel<0, true>,
+                                    tree_attn_bwd_pair_kernel<2, true>, tree_attn_bwd_pair_kernel<4, true>};
   static bool configured = false;
   if (!configured) {
     for (Kernel kf : kernels) DTA_CHECK_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
@@ -775,7 +781,9 @@ int launch(const void* q, const void* k, const void* v, const void* dout, const 
   }
   const char* pe = getenv("DTA_BWD_POLY");                 // same tuning knob as the single-CTA kernel; default 0
   const int poly = pe ? atoi(pe) : 0;
-  const Kernel kernel = kernels[poly <= 0 ? 0 : poly <= 2 ? 1 : 2];
+  const char* hm = getenv("DTA_BWD_HEAD_MAJOR");           // A/B knob (round 2, in-step): see kDefaultPairHeadMajor
+  const bool head_major = hm ? atoi(hm) != 0 : kDefaultPairHeadMajor;
+  const Kernel kernel = kernels[(head_major ? 3 : 0) + (poly <= 0 ? 0 : poly <= 2 ? 1 : 2)];
   if (ev_start) DTA_CHECK_CUDA(cudaEventRecord(ev_start, stream));
   kernel<<<2 * n_pairs * sh->n_kv_heads, kThreads, Smem::total, stream>>>(tq64, tq128, tk, tv, tdo64, tdo128, tdq, taug_l, taug_d, p);
   DTA_CHECK_CUDA(cudaGetLastError());

@@ -26,6 +26,7 @@ gradients accumulate, the shared prefix of a cut is recomputed once per range â€
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Tuple
 
 import torch
@@ -34,7 +35,8 @@ from . import _cabi
 from .attention import use_tree_attention
 from .fused_layers import fused_trunk_forward, supports_fused_trunk
 from .linearize import TrieLayout, linearize_trie
-from .vocab_parallel import logprob_entropy_rows, logprob_entropy_rows_backward
+from .vocab_parallel import (fused_head_supported, lm_head_dlogits_rows, lm_head_logprob_entropy_rows, logprob_entropy_rows,
+                             logprob_entropy_rows_backward)
 
 __all__ = ["TreeTrainingEngine", "_get_forkpos"]
 
@@ -136,10 +138,16 @@ class _TreeHeadLoss(torch.autograd.Function):
         W = weight.detach()
         need_h = hidden.requires_grad
         need_w = weight.requires_grad
-        # With HBM to spare (180 GB on B200) the bf16 logits chunks stay resident between the statistics
-        # pass and the gradient pass, which saves re-running the [rows, hidden] x [hidden, vocab] GEMM.
-        keep = (need_h or need_w) and engine._can_keep_logits(N, W.shape[0], h.element_size(), h.device)
-        lp_nodes, ent_nodes, logz, plan, kept = engine._head_forward(h, W, layout, chunk_rows, keep_logits=keep)
+        fused = engine._use_fused_head(h, W, training=need_h or need_w)
+        if fused:
+            # N1: lm_head fused into the statistics (csrc/head_fwd.cu) -- no logits in HBM, in either pass
+            lp_nodes, ent_nodes, logz, plan = engine._head_forward_fused(h, W, layout, chunk_rows)
+            kept = None
+        else:
+            # With HBM to spare (180 GB on B200) the bf16 logits chunks stay resident between the statistics
+            # pass and the gradient pass, which saves re-running the [rows, hidden] x [hidden, vocab] GEMM.
+            keep = (need_h or need_w) and engine._can_keep_logits(N, W.shape[0], h.element_size(), h.device)
+            lp_nodes, ent_nodes, logz, plan, kept = engine._head_forward(h, W, layout, chunk_rows, keep_logits=keep)
 
         # ---- user loss on per-node vectors (tiny autograd graph) --------------------------
         with torch.enable_grad():
@@ -162,16 +170,21 @@ class _TreeHeadLoss(torch.autograd.Function):
         if need_h or need_w:
             g_lp = torch.zeros_like(lp_nodes) if g_lp is None else g_lp.float()
             g_ent = torch.zeros_like(ent_nodes) if g_ent is None else g_ent.float()
+            dl_buf = torch.empty((min(chunk_rows, N), W.shape[0]), dtype=h.dtype, device=h.device) if fused else None
             for ci, a in enumerate(range(0, N, chunk_rows)):
                 b = min(a + chunk_rows, N)
                 e0, e1 = plan.span(a, b)
-                if kept is not None:
-                    logits, kept[ci] = kept[ci], None
-                else:
-                    logits = h[a:b] @ W.t()
                 row_of = (plan.row[e0:e1] - a).to(torch.int32)
-                logprob_entropy_rows_backward(logits, plan.label[e0:e1], row_of, 1.0, 0, logz[a:b], ent_nodes[a:b],
-                                              g_lp[plan.child[e0:e1]], g_ent[a:b], out=logits)
+                if fused:           # recompute GEMM + log-prob backward in one kernel, gradient chunk in bf16
+                    logits = lm_head_dlogits_rows(h[a:b], W, plan.label[e0:e1], row_of, 1.0, logz[a:b], ent_nodes[a:b],
+                                                  g_lp[plan.child[e0:e1]], g_ent[a:b], out=dl_buf[:b - a])
+                else:
+                    if kept is not None:
+                        logits, kept[ci] = kept[ci], None
+                    else:
+                        logits = h[a:b] @ W.t()
+                    logprob_entropy_rows_backward(logits, plan.label[e0:e1], row_of, 1.0, 0, logz[a:b], ent_nodes[a:b],
+                                                  g_lp[plan.child[e0:e1]], g_ent[a:b], out=logits)
                 if need_h:
                     torch.mm(logits, W, out=dh[a:b])
                 if need_w:
@@ -205,7 +218,15 @@ class TreeTrainingEngine:
         self.head_dim = model_config.head_dim if hasattr(model_config, "head_dim") and model_config.head_dim \
             else model_config.hidden_size // model_config.num_attention_heads
         self.head_chunk_rows = 8192
-        self.keep_head_logits = True     # keep bf16 logits between the head's two passes when HBM allows
+        self.keep_head_logits = True     # (unfused head only) keep bf16 logits between the head's two passes when HBM allows
+        # N1: lm_head fused into the log-prob statistics and their backward (csrc/head_fwd.cu: no logits in HBM).
+        # True / False force it.  None = by measured cost (profiles/r02/head_bench.log, visit12 in-step A/B): the fused
+        # FORWARD beats GEMM + statistics (14.8 vs 21.6 ms at 67k x 151,936) and runs whenever no backward follows
+        # (engine.forward); a training step's backward has to recompute the GEMM without kept logits (2.3 ms per
+        # 8192-row chunk fused, against 1.3 ms on kept logits), which makes the fused step 1 % slower and 17 GB
+        # smaller -- so training uses it when the logits would not fit anyway (_can_keep_logits) and keeps them else.
+        env = os.environ.get("DTA_FUSED_HEAD")
+        self.fused_head: Optional[bool] = None if env is None else env not in ("0", "")
         self.use_fused_trunk = True      # Qwen3-style bf16 models; others go through the HF attention plugin
         self.max_trie_tokens: Optional[int] = None    # None: derive from free HBM (CUDA) / unlimited (elsewhere)
         # Activation recomputation (fused trunk only).  None = automatic: a trie whose full activations exceed the
@@ -321,6 +342,25 @@ class TreeTrainingEngine:
         free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
         return n_rows * vocab * elem + (24 << 30) < free
 
+    def _use_fused_head(self, h: torch.Tensor, W: torch.Tensor, training: bool = False) -> bool:
+        if self.fused_head is False:
+            return False
+        ok = fused_head_supported(h, W)
+        if self.fused_head and not ok:
+            raise _cabi.DtaError("fused_head=True but hidden / lm_head weight are not bf16 CUDA tensors the kernel can address")
+        if self.fused_head is None and training and ok:
+            return not self._can_keep_logits(h.shape[0], W.shape[0], h.element_size(), h.device)
+        return ok
+
+    def _head_forward_fused(self, h: torch.Tensor, W: torch.Tensor, layout: TrieLayout, chunk_rows: int):
+        """``_head_forward`` through the fused lm_head kernel: ONE launch over all rows, no logits."""
+        N = layout.n_nodes
+        plan = _EdgePlan(layout, chunk_rows)
+        x_label, logz, ent_nodes = lm_head_logprob_entropy_rows(h, W, plan.label, plan.row.to(torch.int32), 1.0)
+        lp_nodes = torch.zeros(N, dtype=torch.float32, device=h.device)
+        lp_nodes[plan.child] = x_label - logz[plan.row]
+        return lp_nodes, ent_nodes, logz, plan
+
     def _head_forward(self, h: torch.Tensor, W: torch.Tensor, layout: TrieLayout, chunk_rows: int,
                       keep_logits: bool = False):
         """Per-node log-prob of the edge INTO the node (roots: 0) and per-node entropy
@@ -382,7 +422,10 @@ class TreeTrainingEngine:
         self.last_layout = layout
         h = self._trunk(model, layout)
         _, W = _decoder_and_head(model)
-        lp_nodes, _, _, _, _ = self._head_forward(h, W, layout, self.head_chunk_rows)
+        if self._use_fused_head(h, W):
+            lp_nodes = self._head_forward_fused(h, W, layout, self.head_chunk_rows)[0]
+        else:
+            lp_nodes = self._head_forward(h, W, layout, self.head_chunk_rows)[0]
         for i, attach_list in enumerate(token_trie.attach_lists):
             for attach, length in attach_list:
                 path = layout.path_of_leaf(i, length).long()

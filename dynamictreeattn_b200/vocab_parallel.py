@@ -29,7 +29,8 @@ from torch import distributed as dist
 
 from . import _cabi
 
-__all__ = ["gather_logprobs", "gather_logprobs_entropy", "logprob_entropy_rows"]
+__all__ = ["gather_logprobs", "gather_logprobs_entropy", "logprob_entropy_rows", "lm_head_logprob_entropy_rows",
+           "lm_head_dlogits_rows", "fused_head_supported"]
 
 _DTYPE_CODE = {torch.bfloat16: 0, torch.float32: 1}
 
@@ -243,3 +244,85 @@ def logprob_entropy_rows(x: torch.Tensor, labels: torch.Tensor, row_of: torch.Te
 
 
 logprob_entropy_rows_backward = _backward_logits
+
+
+# ---------------------------------------------------------------------------------------------------------
+# N1: lm_head fused into the statistics -- the [rows, vocab] logits are never materialised (csrc/head_fwd.cu)
+# ---------------------------------------------------------------------------------------------------------
+def lm_head_logprob_entropy_rows(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor,
+                                 row_of: Optional[torch.Tensor], inv_temp: float = 1.0):
+    """(x_label[M], logz[R], entropy[R]) of ``logits = hidden @ weight.T`` WITHOUT the logits: a tcgen05 GEMM whose
+    accumulator tiles are folded into the 16-byte row statistics in the epilogue (reference: HF
+    modeling_qwen3.py:505 + vocab_parallel.py:13-27 over a materialised [B, V] tensor).  hidden [R, K], weight [V, K]
+    bf16 with unit inner stride; ``row_of`` (label -> row; None: one label per row) as in ``logprob_entropy_rows``.
+    The logits behind these numbers are the fp32 accumulators, not their bf16 roundings."""
+    lib = _cabi.load()
+    _cabi.require_cuda(hidden, weight, labels)
+    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise _cabi.DtaError("the fused lm_head kernel takes bf16 hidden states and weights")
+    if hidden.dim() != 2 or weight.dim() != 2 or hidden.shape[1] != weight.shape[1]:
+        raise _cabi.DtaError(f"hidden {tuple(hidden.shape)} and weight {tuple(weight.shape)} do not form a GEMM")
+    if hidden.stride(1) != 1:
+        hidden = hidden.contiguous()
+    if weight.stride(1) != 1:
+        weight = weight.contiguous()
+    R, K = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    labels = labels.reshape(-1).to(torch.int64)
+    M = labels.numel()
+    if row_of is None and M != R:
+        raise _cabi.DtaError(f"labels ({M}) and rows ({R}) disagree")
+    st = _cabi.stream_ptr(dev)
+    with torch.cuda.device(dev):
+        n_split = lib.dta_lm_head_stats_splits(R, V)
+        rows_pad = lib.dta_lm_head_stats_rows_pad(R)
+        stats = torch.empty((n_split, rows_pad, 4), dtype=torch.float32, device=dev)
+        _cabi.check(lib.dta_lm_head_stats(hidden.data_ptr(), hidden.stride(0), weight.data_ptr(), weight.stride(0), R, V,
+                                          K, inv_temp, stats.data_ptr(), st))
+        logz, entropy, _ = _k_finalize(stats.view(n_split, rows_pad * 4), R, False)
+        x_label = torch.empty(M, dtype=torch.float32, device=dev)
+        _cabi.check(lib.dta_lm_head_label_logits(hidden.data_ptr(), hidden.stride(0), weight.data_ptr(), weight.stride(0),
+                                                 K, V, labels.data_ptr(),
+                                                 row_of.data_ptr() if row_of is not None else None, M, inv_temp,
+                                                 x_label.data_ptr(), st))
+    return x_label, logz, entropy
+
+
+def fused_head_supported(hidden: torch.Tensor, weight: torch.Tensor) -> bool:
+    """bf16 CUDA operands the TMA descriptors of csrc/head_fwd.cu can address."""
+    return (hidden.is_cuda and weight.is_cuda and hidden.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
+            and hidden.dim() == 2 and weight.dim() == 2 and hidden.shape[1] == weight.shape[1]
+            and hidden.shape[1] % 64 == 0 and hidden.stride(1) == 1 and weight.stride(1) == 1
+            and hidden.stride(0) % 8 == 0 and weight.stride(0) % 8 == 0
+            and hidden.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0)
+
+
+def lm_head_dlogits_rows(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, row_of: torch.Tensor,
+                         inv_temp: float, logz: torch.Tensor, entropy: torch.Tensor, g_lp: Optional[torch.Tensor],
+                         g_ent: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """d loss / d logits [R, V] (bf16, into ``out``) for ``logits = hidden @ weight.T`` WITHOUT kept logits: the GEMM is
+    recomputed by the fused kernel whose epilogue applies the log-prob / entropy backward; the one-hot terms of the
+    labels (``row_of``: label -> row of this block) are added afterwards.  Counterpart of
+    ``logprob_entropy_rows_backward`` for the fused head."""
+    lib = _cabi.load()
+    R, K = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    st = _cabi.stream_ptr(dev)
+    labels = labels.reshape(-1).to(torch.int64)
+    with torch.cuda.device(dev):
+        rowsum = None
+        if g_lp is not None:
+            g_lp = g_lp.reshape(-1).to(torch.float32).contiguous()
+            rowsum = _k_rowsum(g_lp, row_of, R)
+        if g_ent is not None:
+            g_ent = g_ent.reshape(-1).to(torch.float32).contiguous()
+        _cabi.check(lib.dta_lm_head_dlogits(hidden.data_ptr(), hidden.stride(0), weight.data_ptr(), weight.stride(0), R, V, K,
+                                            inv_temp, logz.data_ptr(), entropy.data_ptr(),
+                                            g_ent.data_ptr() if g_ent is not None else None,
+                                            rowsum.data_ptr() if rowsum is not None else None, out.data_ptr(),
+                                            out.stride(0), st))
+        if g_lp is not None:
+            _k_scatter(out, inv_temp, labels, row_of, g_lp, 0)
+    return out

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTA_ABI_VERSION 4
+#define DTA_ABI_VERSION 5
 #define DTA_TILE 128 /* attention tile edge (queries and keys) */
 
 typedef struct CUstream_st* dta_stream_t;
@@ -205,6 +205,38 @@ int dta_logprob_bwd_scatter(void* dlogits, int dtype, int64_t n_cols, int64_t d_
 /* g_lp_rowsum[row_of[m]] += g_lp[m] (caller zero-fills g_lp_rowsum). */
 int dta_logprob_rowsum_grad(const float* g_lp, const int32_t* row_of, int64_t n_labels, float* g_lp_rowsum,
                             dta_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * lm_head fused into the log-prob / entropy statistics: replaces
+ * `logits = lm_head(hidden)` (HF models/qwen3/modeling_qwen3.py:505) followed by the fp32 log_softmax / entropy of
+ * reference vocab_parallel.py:13-27 WITHOUT materialising the [rows, vocab] logits: a tcgen05 (cta_group::2,
+ * 256 x 256 x 64) GEMM whose accumulator tiles are reduced in the epilogue, straight out of TMEM.
+ * hidden [n_rows, hidden_size], weight [n_cols, hidden_size]: bf16, unit inner stride, row strides in elements
+ * (multiples of 8), 16-byte aligned.  stats: float[n_splits][rows_pad][4] = {m, sum e^(x-m), sum x e^(x-m), 0} per
+ * vocab split and row, n_splits = dta_lm_head_stats_splits(n_rows, n_cols), rows_pad =
+ * dta_lm_head_stats_rows_pad(n_rows); merge with dta_logprob_finalize(stats, n_splits, 4 * rows_pad, n_rows, ...).
+ * ------------------------------------------------------------------------------------- */
+int dta_lm_head_stats_splits(int64_t n_rows, int64_t n_cols);
+int64_t dta_lm_head_stats_rows_pad(int64_t n_rows);
+int dta_lm_head_stats(const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride, int64_t n_rows,
+                      int64_t n_cols, int hidden_size, float inv_temperature, float* stats, dta_stream_t stream);
+
+/* Backward of the same fusion: the SAME GEMM mainloop recomputes each logits tile and the epilogue turns it into
+ * d loss / d logits (formula of dta_logprob_bwd, without the one-hot label terms: add them with
+ * dta_logprob_bwd_scatter), stored in bf16: dlogits[n_rows][d_row_stride].  The reference keeps the fp32 softmax for
+ * this (vocab_parallel.py:312-318); here neither logits nor softmax exist between the passes.  The caller then forms
+ * d hidden = dlogits W and d W = dlogits^T hidden with library GEMMs, row chunk by row chunk. */
+int dta_lm_head_dlogits(const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride, int64_t n_rows,
+                        int64_t n_cols, int hidden_size, float inv_temperature, const float* logz, const float* entropy,
+                        const float* g_entropy, const float* g_lp_rowsum, void* dlogits, int64_t d_row_stride,
+                        dta_stream_t stream);
+
+/* x_label[m] = inv_temperature * <hidden[row_of[m]], weight[labels[m]]>: the logit of one (row, label) edge without
+ * the logits row (fp32 accumulation of bf16 products).  row_of == NULL: row_of[m] = m; row_of[m] < 0 or a label
+ * outside [0, n_cols) yields 0. */
+int dta_lm_head_label_logits(const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride,
+                             int hidden_size, int64_t n_cols, const int64_t* labels, const int32_t* row_of,
+                             int64_t n_labels, float inv_temperature, float* x_label, dta_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused layer kernels either side of attention — replace the ATen

@@ -70,12 +70,27 @@ def test_device_linearisation_called_and_launches_counted():
     seqs = synth_trie(12, 64, (2, 2), (30, 60), vocab=2048)
     before = dict(_cabi.call_count)
     eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 8192)
+    eng.fused_head = True
     trie = TokenTrie(seqs, [{"w_logprobs": -1.0, "w_entropy": 0.1} for _ in seqs])
     eng.backward(model, trie, tree_oracle.example_loss, block_size=2048)
     delta = {k: _cabi.call_count.get(k, 0) - before.get(k, 0) for k in _cabi.call_count}
     assert delta["dta_trie_linearize"] == 1 and delta["dta_tile_meta"] == 1
     assert delta["dta_tree_attn_fwd"] == 2 and delta["dta_tree_attn_bwd"] == 2        # one per layer
-    assert delta["dta_logprob_row_stats"] >= 1 and delta["dta_logprob_bwd"] >= 1
+    # the head runs fused (N1): one statistics launch over all rows, one fused recompute + backward launch per row chunk
+    assert delta["dta_lm_head_stats"] == 1 and delta["dta_lm_head_dlogits"] >= 1 and delta["dta_lm_head_label_logits"] == 1
+    assert delta.get("dta_logprob_row_stats", 0) == 0 and delta.get("dta_logprob_bwd", 0) == 0
+    # default policy: a training step keeps bf16 logits while they fit (faster backward), a forward-only call is fused
+    auto = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 8192)
+    assert auto.fused_head is None
+    before = dict(_cabi.call_count)
+    trie = TokenTrie(seqs, [{"w_logprobs": -1.0, "w_entropy": 0.1} for _ in seqs])
+    auto.backward(model, trie, tree_oracle.example_loss, block_size=2048)
+    delta = {k: _cabi.call_count.get(k, 0) - before.get(k, 0) for k in _cabi.call_count}
+    assert delta["dta_logprob_row_stats"] >= 1 and delta["dta_logprob_bwd"] >= 1 and delta.get("dta_lm_head_stats", 0) == 0
+    before = dict(_cabi.call_count)
+    auto.forward(model, TokenTrie(seqs))
+    delta = {k: _cabi.call_count.get(k, 0) - before.get(k, 0) for k in _cabi.call_count}
+    assert delta["dta_lm_head_stats"] == 1 and delta.get("dta_logprob_row_stats", 0) == 0
 
 
 def test_dense_module_matches_oracle_and_tree():
@@ -150,6 +165,38 @@ def test_memory_bounded_ranges_on_device_and_default_budget():
     assert abs(loss1 - loss2) < 0.01 * abs(loss1)
     worst = max(((g2[n] - g1[n]).norm() / (g1[n].norm() + 1e-6)).item() for n in g1)
     assert worst < 6e-2, worst
+
+
+def test_fused_head_equals_materialised_logits_head():
+    """N1 in the engine: the fused lm_head path (no logits in HBM) and the cuBLAS + row-kernel path over materialised
+    bf16 logits give the same loss and gradients up to the bf16 rounding of the logits; both within the tolerance of
+    the fp32 oracle; forward-only log-probs agree as well."""
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    from dynamictreeattn_b200.tree_training_engine import TreeTrainingEngine
+    cfg, ref, model = _models()
+    seqs = synth_trie(14, 80, (3, 2), (40, 100), vocab=2048)
+    attachs = [{"w_logprobs": -1.0, "w_entropy": 0.1} for _ in seqs]
+    loss_ref = tree_oracle.dense_backward(ref, seqs, [dict(a) for a in attachs], tree_oracle.example_loss)
+    out = {}
+    for fused in (True, False):
+        model.zero_grad(set_to_none=True)
+        eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 8192)
+        eng.fused_head = fused
+        eng.head_chunk_rows = 128                   # several row chunks in the head's backward
+        trie = TokenTrie(seqs, [dict(a) for a in attachs])
+        trie.backward_permute()
+        loss = eng.backward(model, trie, tree_oracle.example_loss, block_size=None)
+        r = _ratios(model, ref)
+        assert abs(loss - loss_ref) < 0.02 * abs(loss_ref), (fused, loss, loss_ref)
+        assert r[-1] < 1.1e-1 and r[len(r) // 2] < 3e-2, (fused, r[-1], r[len(r) // 2])
+        ftrie = TokenTrie(seqs)
+        ftrie.forward_permute()
+        out[fused] = (loss, {n: p.grad.float().clone() for n, p in model.named_parameters()}, eng.forward(model, ftrie))
+    assert abs(out[True][0] - out[False][0]) < 5e-3 * abs(loss_ref)
+    worst = max(((out[True][1][n] - g).norm() / (g.norm() + 1e-6)).item() for n, g in out[False][1].items())
+    assert worst < 3e-2, worst
+    for a, b in zip(out[True][2], out[False][2]):
+        assert (a - b).abs().max().item() < 5e-2
 
 
 def test_layer_recompute_same_gradients_less_memory():

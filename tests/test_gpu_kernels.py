@@ -247,6 +247,86 @@ def test_logprob_rows_with_edge_labels():
     assert ((got - xr.grad).norm() / xr.grad.norm()).item() < 6e-3
 
 
+@pytest.mark.parametrize("R,K,V,temp", [(300, 256, 1003, 1.0), (513, 1024, 151936, 1.0), (4096, 2048, 18992, 0.7),
+                                        (1, 64, 5, 1.0), (2500, 1024, 151936, 1.3)])
+def test_fused_lm_head_statistics(R, K, V, temp):
+    """N1: lm_head fused into the log-prob / entropy statistics (csrc/head_fwd.cu, tcgen05 cta_group::2 GEMM with the
+    online-softmax epilogue) against the fp32 definition logits = hidden W^T -> log_softmax / entropy / gather on the
+    SAME bf16 inputs (reference HF modeling_qwen3.py:505 + vocab_parallel.py:13-27): ragged rows (not a multiple of
+    256), a ragged last vocab tile, several labels per row, rows without labels."""
+    from dynamictreeattn_b200.vocab_parallel import lm_head_logprob_entropy_rows
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(R + V)
+    h = torch.randn(R, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(V, K, device="cuda", generator=g) * (3.0 / K ** 0.5)).bfloat16()
+    M = 2 * R + 3
+    row_of = torch.randint(0, R, (M,), device="cuda", generator=g).to(torch.int32)
+    row_of[0] = -1
+    labels = torch.randint(0, V, (M,), device="cuda", generator=g)
+    xl, lz, ent = lm_head_logprob_entropy_rows(h, w, labels, row_of, 1.0 / temp)
+    want_lz = torch.empty(R, device="cuda", dtype=torch.float64)
+    want_ent = torch.empty(R, device="cuda", dtype=torch.float64)
+    want_xl = torch.zeros(M, device="cuda", dtype=torch.float64)
+    for a in range(0, R, 512):                                      # fp64 reference, a block of rows at a time
+        z = (h[a:a + 512].double() @ w.double().t()) / temp
+        lsm = torch.log_softmax(z, -1)
+        want_lz[a:a + 512] = torch.logsumexp(z, -1)
+        want_ent[a:a + 512] = -(lsm.exp() * lsm).sum(-1)
+        sel = (row_of >= a) & (row_of < a + 512)
+        want_xl[sel] = z[row_of[sel].long() - a, labels[sel]]
+    # against fp64: the tensor core's fp32 accumulation of K bf16 products + ex2.approx leave a few 1e-6 RELATIVE on
+    # |logz| ~ 16-18 (measured 2.5e-5 .. 5.7e-5 absolute, K = 1024 .. 2048); the row kernels' 1e-5 bound is for a
+    # log-softmax of GIVEN logits, here the GEMM is part of the op
+    assert (lz.double() - want_lz).abs().max().item() < 1e-4
+    assert (ent.double() - want_ent).abs().max().item() < 3e-4
+    assert (xl.double() - want_xl).abs().max().item() < 1e-4
+    # one label per row
+    lab1 = torch.randint(0, V, (R,), device="cuda", generator=g)
+    xl1, lz1, _ = lm_head_logprob_entropy_rows(h, w, lab1, None, 1.0 / temp)
+    assert torch.equal(lz1, lz)
+    z_lab = (h.double() * w[lab1].double()).sum(-1) / temp
+    assert (xl1.double() - z_lab).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("R,K,V,temp", [(300, 256, 1003, 1.0), (700, 1024, 151936, 1.0), (1500, 2048, 18992, 0.7)])
+def test_fused_lm_head_backward(R, K, V, temp):
+    """The backward of the fusion (dta_lm_head_dlogits: recompute GEMM + log-prob / entropy backward in the epilogue,
+    bf16 gradient, then the one-hot scatter) against fp32 autograd through logits = hidden W^T -> log_softmax on the
+    same bf16 inputs, with several labels per row and rows without labels; one bf16 rounding of the result."""
+    from dynamictreeattn_b200.vocab_parallel import lm_head_dlogits_rows, lm_head_logprob_entropy_rows
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(R + V + 1)
+    h = torch.randn(R, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(V, K, device="cuda", generator=g) * (3.0 / K ** 0.5)).bfloat16()
+    M = 2 * R
+    row_of = torch.randint(0, R, (M,), device="cuda", generator=g).to(torch.int32)
+    labels = torch.randint(0, V, (M,), device="cuda", generator=g)
+    key = row_of.long() * V + labels                                   # (row, label) pairs must be unique (trie edges are)
+    keep = torch.ones(M, dtype=torch.bool, device="cuda")
+    order = torch.argsort(key)
+    dup = torch.zeros(M, dtype=torch.bool, device="cuda")
+    dup[order[1:]] = key[order[1:]] == key[order[:-1]]
+    keep &= ~dup
+    row_of, labels = row_of[keep].contiguous(), labels[keep].contiguous()
+    M = int(labels.numel())
+    g_lp = torch.randn(M, device="cuda", generator=g)
+    g_ent = torch.randn(R, device="cuda", generator=g)
+    _, lz, ent = lm_head_logprob_entropy_rows(h, w, labels, row_of, 1.0 / temp)
+    out = torch.empty(R, V, device="cuda", dtype=torch.bfloat16)
+    lm_head_dlogits_rows(h, w, labels, row_of, 1.0 / temp, lz, ent, g_lp, g_ent, out)
+    want = torch.empty(R, V, device="cuda")
+    for a in range(0, R, 512):
+        b = min(a + 512, R)
+        z = (h[a:b].float() @ w.float().t()).requires_grad_(True)
+        lsm = torch.log_softmax(z / temp, -1)
+        sel = (row_of >= a) & (row_of < b)
+        loss = (lsm[row_of[sel].long() - a, labels[sel]] * g_lp[sel]).sum() + (-(lsm.exp() * lsm).sum(-1) * g_ent[a:b]).sum()
+        loss.backward()
+        want[a:b] = z.grad
+    assert ((out.float() - want).norm() / want.norm()).item() < 6e-3
+    assert (out.float() - want).abs().max().item() < 2e-2 * want.abs().max().item() + 1e-6
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_vocab_shard_merge_equals_unsharded(world):
     """BASELINE config 4 algebra on one GPU: per-shard 16-byte row statistics merged by
