@@ -541,8 +541,12 @@ def run_ours(args):
     sum_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.SUM)     # noqa: E731
 
     # ---- cost model: refit on this box from timed steps (every rank times the same steps; rank 0's fit is used) ----
-    tm, tm_info = calibrate_time_model(engine, model, dev)
-    if world > 1:
+    if args.no_calibrate:
+        from dynamictreeattn_b200.tree_time_model import TreeTimeModel
+        tm, tm_info = TreeTimeModel(), {"samples": 0, "note": "--no-calibrate: unfitted model (pred = n_tree_tokens)"}
+    else:
+        tm, tm_info = calibrate_time_model(engine, model, dev)
+    if world > 1 and tm.coeffs is not None:
         c = torch.tensor(tm.coeffs, dtype=torch.float64, device=dev)
         dist.broadcast(c, 0)
         tm.coeffs = np.array(c.tolist())
@@ -758,8 +762,7 @@ def run_ours(args):
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     pair_on = layout.bwd_whole_tiles(cfg.num_key_value_heads, n_sm) if pair_env == "auto" else pair_env not in ("", "0")
     bwd_kernel = "tree_attn_bwd_pair_kernel" if pair_on else "tree_attn_bwd_kernel"
-    traffic = load_ncu_traffic("tree_attn_bwd_kernel", pairs_local) if world == 1 and not pair_on else \
-        {"value": None, "source": None, "captured": None}
+    traffic = load_ncu_traffic(bwd_kernel, pairs_local) if world == 1 else {"value": None, "source": None, "captured": None}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -786,6 +789,7 @@ def run_ours(args):
             "peak_note": "`peak`/`frac` use the SUSTAINED measured bf16 figure (the kernel is timed inside a long, "
                          "power-capped step); `frac_burst` is against the burst figure SURVEY.md section 8d names",
             "traffic": traffic["value"], "traffic_source": traffic["source"], "traffic_captured": traffic["captured"],
+            "traffic_file": traffic.get("capture_file"),
             "traffic_note": "DRAM bytes per launch, ncu --set full of the same kernel on the same trie, a STATIC capture "
                             "(not measured in this run); algorithmic minimum ~1.7 GB (q,k,v,o,dO read once, dq/dk/dv + fp32 "
                             "dq accumulator written): Q/dO tiles are re-read per key tile from L2, the kernel is bound by "
@@ -825,6 +829,7 @@ def main():
     ap.add_argument("--no-dense-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-calibrate", action="store_true", help="skip the 16 timed steps that refit the cost model (ncu launch lists)")
     ap.add_argument("--no-vocab-parallel", action="store_true")
     ap.add_argument("--vocab-parallel-only", action="store_true",
                     help="BASELINE config 4 alone: torchrun --nproc-per-node {2,4,8} bench.py --vocab-parallel-only")

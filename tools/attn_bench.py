@@ -53,7 +53,19 @@ def run_case(name, seqs, iters, Hq=16, Hkv=8, permute="backward"):
     bwd = [a.elapsed_time(b) for kind, a, b in attention.PROFILE if kind == "bwd"]
     attention.PROFILE = None
     f, b = statistics.median(fwd), statistics.median(bwd)
-    res = {"case": name, "N": N, "leaves": lay.n_leaf, "pairs": P, "fwd_ms": round(f, 3), "bwd_ms": round(b, 3),
+    # tile density: visible pairs / (live 128 x 128 tile pairs x 128^2) -- how much of the tensor work the kernels issue
+    # is unmasked (the TFLOP/s below count ONLY visible pairs); partial = live tiles that need the per-element mask
+    live = int(lay.q_nlive.sum().item())
+    n_t = lay.n_pad // 128
+    kmin = lay.kmin_end.cpu()
+    kmax = lay.kmax_end.cpu()
+    full = 0
+    for qt in range(n_t):
+        q0, q1 = qt * 128, qt * 128 + 128
+        full += int(((kmax[:qt] > q0) & (kmin[:qt] >= q1)).sum())
+    res = {"case": name, "N": N, "leaves": lay.n_leaf, "pairs": P, "live_tiles": live,
+           "tile_density": round(P / (live * 16384.0), 4), "partial_tile_share": round(1.0 - full / max(live, 1), 4),
+           "fwd_ms": round(f, 3), "bwd_ms": round(b, 3),
            "fwd_min_ms": round(min(fwd), 3), "bwd_min_ms": round(min(bwd), 3),
            "fwd_tflops": round(4 * P * Hq * 128 / f / 1e9, 1), "bwd_tflops": round(10 * P * Hq * 128 / b / 1e9, 1),
            "fwd_bwd_tflops": round(14 * P * Hq * 128 / (f + b) / 1e9, 1)}
