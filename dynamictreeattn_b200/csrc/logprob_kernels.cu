@@ -9,12 +9,12 @@
 #include "dta_common.cuh"
 #include "../../include/dta_b200.h"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace dta {
 
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kLn2 = 0.6931471805599453f;
-static constexpr int kRowThreads = 512;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -73,7 +73,7 @@ template <> struct Vec<float> {
 // ------------------------------------------------------------------------------------
 // forward: per-row online softmax statistics
 // ------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int kRowThreads>
 __global__ void __launch_bounds__(kRowThreads) row_stats_kernel(const T* __restrict__ logits, int64_t n_rows,
                                                                int64_t n_cols, int64_t row_stride, float inv_temp,
                                                                const int64_t* __restrict__ labels, int64_t vocab_start,
@@ -95,12 +95,14 @@ __global__ void __launch_bounds__(kRowThreads) row_stats_kernel(const T* __restr
     RowStat st{-INFINITY, 0.f, 0.f};
     const bool vec_ok = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
     const int64_t n_vec = vec_ok ? n_cols / V : 0;
-    for (int64_t v0 = static_cast<int64_t>(threadIdx.x) * U; v0 < n_vec; v0 += static_cast<int64_t>(kRowThreads) * U) {
+    // vector u of a thread is kRowThreads vectors further along the row: every load instruction of a warp covers 512
+    // contiguous bytes (a thread-contiguous mapping fetched each 32-byte sector twice)
+    for (int64_t v0 = threadIdx.x; v0 < n_vec; v0 += static_cast<int64_t>(kRowThreads) * U) {
       float x[U * V];
       int cnt = 0;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (v0 + u < n_vec) { Vec<T>::load(p + (v0 + u) * V, x + u * V); cnt = (u + 1) * V; }
+        if (v0 + u * kRowThreads < n_vec) { Vec<T>::load(p + (v0 + u * kRowThreads) * V, x + u * V); cnt = (u + 1) * V; }
       }
       float mx = -INFINITY;
 #pragma unroll
@@ -190,7 +192,7 @@ __global__ void finalize_kernel(const float4* __restrict__ stats_all, int world,
 // ------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int kRowThreads>
 __global__ void __launch_bounds__(kRowThreads) logprob_bwd_kernel(const T* __restrict__ logits, int64_t n_rows,
                                                                  int64_t n_cols, int64_t row_stride, float inv_temp,
                                                                  const float* __restrict__ logz,
@@ -215,26 +217,27 @@ __global__ void __launch_bounds__(kRowThreads) logprob_bwd_kernel(const T* __res
     const float hot = inv_temp * G;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(q)) & 15) == 0;
     const int64_t n_vec = vec_ok ? n_cols / V : 0;
-    for (int64_t v0 = static_cast<int64_t>(threadIdx.x) * U; v0 < n_vec; v0 += static_cast<int64_t>(kRowThreads) * U) {
+    for (int64_t v0 = threadIdx.x; v0 < n_vec; v0 += static_cast<int64_t>(kRowThreads) * U) {
       float x[U * V];
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (v0 + u < n_vec) Vec<T>::load(p + (v0 + u) * V, x + u * V);
+        if (v0 + u * kRowThreads < n_vec) Vec<T>::load(p + (v0 + u * kRowThreads) * V, x + u * V);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (v0 + u < n_vec) {
+        if (v0 + u * kRowThreads < n_vec) {
 #pragma unroll
           for (int i = 0; i < V; ++i) {
             const float lp2 = fmaf(x[u * V + i], c, -lz2);  // log2 p
             const float pr = ex2(lp2);
             x[u * V + i] = inv_temp * pr * fmaf(-a * kLn2, lp2, k0);
           }
-          if (static_cast<uint64_t>(lc - (v0 + u) * V) < static_cast<uint64_t>(V)) {
+          const int64_t e0 = (v0 + u * kRowThreads) * V;           // first element of this vector
+          if (static_cast<uint64_t>(lc - e0) < static_cast<uint64_t>(V)) {
 #pragma unroll
             for (int i = 0; i < V; ++i)
-              if ((v0 + u) * V + i == lc) x[u * V + i] += hot;
+              if (e0 + i == lc) x[u * V + i] += hot;
           }
-          Vec<T>::store(q + (v0 + u) * V, x + u * V);
+          Vec<T>::store(q + e0, x + u * V);
         }
       }
     }
@@ -275,9 +278,25 @@ static int small_grid(int64_t n, int threads) {
   const int64_t cap = 16 * static_cast<int64_t>(sm_count());
   return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
 }
-static int row_grid(int64_t n_rows) {
-  const int64_t cap = 8 * static_cast<int64_t>(sm_count());  // grid-stride over rows; multiple of SM count
+static int row_grid(int64_t n_rows, int threads) {
+  const int64_t cap = (8 * 512 / threads) * static_cast<int64_t>(sm_count());  // grid-stride over rows; multiple of SM count
   return static_cast<int>(n_rows < cap ? n_rows : cap);
+}
+// Threads per row (= per block).  Measured on the B200 with the coalesced vector mapping (profiles/r02/logprob_threads_ab.log):
+// the forward is latency-bound on its online-softmax chain and likes MANY small blocks (64-128 threads: 4.6 TB/s at
+// 151,936 columns, 4.2-4.5 TB/s on vocab-parallel shards; 512 threads: 3.9 / 2.2-2.9); the backward is a pure stream
+// and holds 5.8-6.0 TB/s (88-92 % of the measured copy bandwidth) from 64 to 256 threads.  DTA_LOGPROB_THREADS forces one
+// size for both (A/B knob).
+static int row_threads(bool backward, int64_t n_cols) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("DTA_LOGPROB_THREADS");
+    const int v = e ? atoi(e) : 0;
+    forced = (v == 32 || v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) ? v : 0;
+  }
+  if (forced) return forced;
+  if (backward) return 256;
+  return n_cols >= 65536 ? 128 : 64;
 }
 
 }  // namespace dta
@@ -295,13 +314,30 @@ int dta_logprob_row_stats(const void* logits, int dtype, int64_t n_rows, int64_t
   if (n_rows == 0) return DTA_OK;
   DTA_REQUIRE(logits && stats, "NULL pointer argument");
   DTA_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 15) == 0, "stats must be 16-byte aligned");
-  if (dtype == 0)
-    row_stats_kernel<__nv_bfloat16><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(logits), n_rows, n_cols, row_stride, inv_temperature, labels, vocab_start,
-        stats);
-  else
-    row_stats_kernel<float><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
-        static_cast<const float*>(logits), n_rows, n_cols, row_stride, inv_temperature, labels, vocab_start, stats);
+  const int th = row_threads(false, n_cols);
+#define DTA_ROW_STATS(T, TH)                                                                                       \
+  row_stats_kernel<T, TH><<<row_grid(n_rows, TH), TH, 0, stream>>>(static_cast<const T*>(logits), n_rows, n_cols, \
+                                                                   row_stride, inv_temperature, labels, vocab_start, stats)
+  if (dtype == 0) {
+    switch (th) {
+      case 32: DTA_ROW_STATS(__nv_bfloat16, 32); break;
+      case 64: DTA_ROW_STATS(__nv_bfloat16, 64); break;
+      case 128: DTA_ROW_STATS(__nv_bfloat16, 128); break;
+      case 256: DTA_ROW_STATS(__nv_bfloat16, 256); break;
+      case 1024: DTA_ROW_STATS(__nv_bfloat16, 1024); break;
+      default: DTA_ROW_STATS(__nv_bfloat16, 512);
+    }
+  } else {
+    switch (th) {
+      case 32: DTA_ROW_STATS(float, 32); break;
+      case 64: DTA_ROW_STATS(float, 64); break;
+      case 128: DTA_ROW_STATS(float, 128); break;
+      case 256: DTA_ROW_STATS(float, 256); break;
+      case 1024: DTA_ROW_STATS(float, 1024); break;
+      default: DTA_ROW_STATS(float, 512);
+    }
+  }
+#undef DTA_ROW_STATS
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
 }
@@ -347,14 +383,31 @@ int dta_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t n_col
   if (n_rows == 0) return DTA_OK;
   DTA_REQUIRE(logits && logz && entropy && dlogits, "NULL pointer argument");
   DTA_REQUIRE(labels == nullptr || g_lp_rowsum != nullptr, "labels (one per row) need the per-row g_lp in g_lp_rowsum");
-  if (dtype == 0)
-    logprob_bwd_kernel<__nv_bfloat16><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(logits), n_rows, n_cols, row_stride, inv_temperature, logz, entropy,
-        g_entropy, g_lp_rowsum, labels, vocab_start, static_cast<__nv_bfloat16*>(dlogits), d_row_stride);
-  else
-    logprob_bwd_kernel<float><<<row_grid(n_rows), kRowThreads, 0, stream>>>(
-        static_cast<const float*>(logits), n_rows, n_cols, row_stride, inv_temperature, logz, entropy, g_entropy,
-        g_lp_rowsum, labels, vocab_start, static_cast<float*>(dlogits), d_row_stride);
+  const int th = row_threads(true, n_cols);
+#define DTA_ROW_BWD(T, TH)                                                                                              \
+  logprob_bwd_kernel<T, TH><<<row_grid(n_rows, TH), TH, 0, stream>>>(                                                  \
+      static_cast<const T*>(logits), n_rows, n_cols, row_stride, inv_temperature, logz, entropy, g_entropy, g_lp_rowsum, \
+      labels, vocab_start, static_cast<T*>(dlogits), d_row_stride)
+  if (dtype == 0) {
+    switch (th) {
+      case 32: DTA_ROW_BWD(__nv_bfloat16, 32); break;
+      case 64: DTA_ROW_BWD(__nv_bfloat16, 64); break;
+      case 128: DTA_ROW_BWD(__nv_bfloat16, 128); break;
+      case 256: DTA_ROW_BWD(__nv_bfloat16, 256); break;
+      case 1024: DTA_ROW_BWD(__nv_bfloat16, 1024); break;
+      default: DTA_ROW_BWD(__nv_bfloat16, 512);
+    }
+  } else {
+    switch (th) {
+      case 32: DTA_ROW_BWD(float, 32); break;
+      case 64: DTA_ROW_BWD(float, 64); break;
+      case 128: DTA_ROW_BWD(float, 128); break;
+      case 256: DTA_ROW_BWD(float, 256); break;
+      case 1024: DTA_ROW_BWD(float, 1024); break;
+      default: DTA_ROW_BWD(float, 512);
+    }
+  }
+#undef DTA_ROW_BWD
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
 }
