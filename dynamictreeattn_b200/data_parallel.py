@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from .token_trie import TokenTrie
-from .trie import CompressedTrie, _get_stats, _get_subtrie
+from .trie import CompressedTrie, _get_range_subtrie, _get_stats, _get_subtrie
 
 __all__ = [
     "LB_by_n_tokens", "LB_by_TM", "LB_by_DFS_and_TM", "pred_time", "get_original_bins",
@@ -85,12 +85,14 @@ def LB_by_TM(token_seqs, time_model, args) -> List[List[int]]:
     return get_original_bins(token_trie, leaf_bins)
 
 
-def try_devide(compressed_trie, n_seqs, args, divL, divR, time_model, cost_limit: float):
+def try_devide(compressed_trie, n_seqs, args, divL, divR, time_model, cost_limit: float, _cost_cache=None):
     """Cut DFS-ordered leaves into consecutive runs of predicted cost <= cost_limit.
 
     Returns the run start indices; more than K of them means the limit is
     infeasible.  ``divL``/``divR`` bracket each cut from earlier probes
-    (data_parallel.py:58-79).
+    (data_parallel.py:58-79).  ``_cost_cache`` (optional dict): predicted cost of a leaf range, shared by the probes
+    of one ``LB_by_DFS_and_TM`` call -- the outer bisection asks for the same (start, end) ranges again and again; a
+    pure memo, so the cuts are the reference's bit for bit.
     """
     K = args.K
     cuts: List[int] = []
@@ -103,8 +105,13 @@ def try_devide(compressed_trie, n_seqs, args, divL, divR, time_model, cost_limit
         hi = divR[len(cuts)] - 1
         while lo < hi:
             mid = (lo + hi + 1) // 2
-            sub = _get_subtrie(compressed_trie, set(range(start, mid + 1)))
-            if pred_time(sub, time_model, args.mode, args.block_size) <= cost_limit:
+            cost = _cost_cache.get((start, mid)) if _cost_cache is not None else None
+            if cost is None:
+                sub = _get_range_subtrie(compressed_trie, start, mid + 1)      # == _get_subtrie(trie, set(range(start, mid + 1)))
+                cost = pred_time(sub, time_model, args.mode, args.block_size)
+                if _cost_cache is not None:
+                    _cost_cache[(start, mid)] = cost
+            if cost <= cost_limit:
                 lo = mid
             else:
                 hi = mid - 1
@@ -129,9 +136,10 @@ def LB_by_DFS_and_TM(token_seqs, time_model, args) -> List[List[int]]:
 
     divL = [0] * (K + 1)
     divR = [n_leaf] * (K + 1)
+    cache: dict = {}
     while hi - lo > eps:
         mid = (lo + hi) / 2.0
-        cuts = try_devide(full, n_leaf, args, divL, divR, time_model, mid)
+        cuts = try_devide(full, n_leaf, args, divL, divR, time_model, mid, cache)
         if len(cuts) <= K:
             hi = mid
             divR[: len(cuts)] = cuts

@@ -20,7 +20,7 @@ from __future__ import annotations
 import random
 from typing import Callable, Iterable, List, Optional, Sequence, Tuple
 
-__all__ = ["_get_stats", "CompressedTrie", "_get_subtrie", "tree_pair_count"]
+__all__ = ["_get_stats", "CompressedTrie", "_get_subtrie", "_get_range_subtrie", "tree_pair_count"]
 
 
 def _ceil_div(a: int, b: int) -> int:
@@ -114,6 +114,8 @@ class CompressedTrie:
     def __init__(self, lens: Sequence[int], lcp_lens: Sequence[int]):
         if len(lcp_lens) != len(lens) - 1:
             raise ValueError("lcp_lens的长度必须为len(lens)-1 (len(lcp_lens) must be len(lens)-1)")
+        self.leaf_lens = list(lens)          # the DFS-ordered leaves this trie was built from
+        self.leaf_lcps = list(lcp_lens)
         self.depth: List[int] = [0]
         self.seq_id: List[int] = [-1]
         self.children: List[List[int]] = [[]]
@@ -262,3 +264,10 @@ class CompressedTrie:
 def _get_subtrie(trie: CompressedTrie, seq_set) -> CompressedTrie:
     lens, lcp_lens = trie.get_lens(seq_set)
     return CompressedTrie(lens, lcp_lens)
+
+
+def _get_range_subtrie(trie: CompressedTrie, start: int, end: int) -> CompressedTrie:
+    """``_get_subtrie(trie, set(range(start, end)))`` for a CONTIGUOUS range of the trie's own (DFS-ordered) leaves:
+    nothing is skipped between two kept leaves, so the sub-trie's lens / lcp_lens are slices of the trie's inputs and
+    the O(n_leaf) walk of ``get_lens`` is not needed (same result, asserted by tests/test_host_golden.py)."""
+    return CompressedTrie(trie.leaf_lens[start:end], trie.leaf_lcps[start:end - 1])

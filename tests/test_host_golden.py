@@ -101,6 +101,22 @@ def test_linearisation_identities(idx):
         assert lin["depth"][lin["paths"][i]].tolist() == list(range(len(ids)))
 
 
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_range_subtrie_equals_subset_subtrie(idx):
+    """The partitioner's shortcut for contiguous leaf ranges builds the same sub-trie as the reference's
+    _get_subtrie(trie, set(range(a, b))) (data_parallel.py:67-70, trie.py:240-242)."""
+    from dynamictreeattn_b200.trie import _get_range_subtrie
+    c = CASES[idx]
+    t = TokenTrie(_seqs(c))
+    full = CompressedTrie(t.lens, t.lcp_lens)
+    n = len(t.lens)
+    for a in range(n):
+        for b in range(a + 1, n + 1):
+            x, y = _get_subtrie(full, set(range(a, b))), _get_range_subtrie(full, a, b)
+            assert (x.depth, x.seq_id, x.children) == (y.depth, y.seq_id, y.children)
+            assert x.get_order_backward() == y.get_order_backward()
+
+
 def test_time_model_matches_reference():
     g = json.loads((GOLDEN / "time_model.json").read_text())
     tm = TreeTimeModel()
