@@ -79,7 +79,7 @@ struct Params {
   // (docs/next_kernels.md 1.2); DTA_PAIR_DRAIN_LANE picks another lane for the A/B (any lane may arrive after the
   // __syncwarp).  Default 0 = the measured configuration.
   int drain_lane;
-  int handoff_commit;          // 1: the three hand-offs to the leader use commit_signal_leader instead of a remote arrive
+  int handoff_commit;          // bit mask (P^T, dS^T, R1 free): that hand-off to the leader uses commit_signal_leader instead of a remote arrive
   long long* trace;            // debug timeline (NULL in production): [step < 48][cluster rank][16] clock64 stamps of cluster 0
 };
 
@@ -219,6 +219,7 @@ __device__ __forceinline__ void pwait_cluster(uint64_t* bar, uint32_t parity) { 
 // kHeadMajor: launch order -- every key-tile pair of KV head 0, then head 1, ... (Q / dO / dQ of one head pair in L2 at a
 // time) instead of the KV heads of a pair side by side; compile-time so that the step loop's code is the same
 static constexpr bool kDefaultPairHeadMajor = false;
+static constexpr int kDefaultHandoff = 0;            // bit mask of hand-offs sent as commit signals (see Params::handoff_commit)
 template <int kPolyOf8, bool kHeadMajor>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __grid_constant__ CUtensorMap tmap_q128,
@@ -545,7 +546,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (p.handoff_commit) commit_signal_leader(bar_p_full); else mbar_arrive_cluster(p_full_l);
+        if (p.handoff_commit & 1) commit_signal_leader(bar_p_full); else mbar_arrive_cluster(p_full_l);
       }
       if (threadIdx.x == 0) DTA_PTRACE(7);
 
@@ -578,7 +579,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_ds_full);
-        if (p.handoff_commit) commit_signal_leader(bar_ds_pair); else mbar_arrive_cluster(ds_pair_l);
+        if (p.handoff_commit & 2) commit_signal_leader(bar_ds_pair); else mbar_arrive_cluster(ds_pair_l);
       }
       if (threadIdx.x == 0) DTA_PTRACE(9);
     }
@@ -630,7 +631,7 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
       tc_fence_before();
       __syncwarp();
       if (lane == p.drain_lane) {
-        if (p.handoff_commit) commit_signal_leader(bar_r1_free); else mbar_arrive_cluster(r1_free_l);
+        if (p.handoff_commit & 4) commit_signal_leader(bar_r1_free); else mbar_arrive_cluster(r1_free_l);
       }
       if (threadIdx.x == 256) DTA_PTRACE(11);
       float* stage = reinterpret_cast<float*>(smem + Smem::dq_stage) + (warp & 3) * (kDqBufs * kDqRows * 32);
@@ -767,7 +768,9 @@ int launch(const void* q, const void* k, const void* v, const void* dout, const 
   const char* dl = getenv("DTA_PAIR_DRAIN_LANE");
   p.drain_lane = dl ? (atoi(dl) & 31) : 0;
   const char* ho = getenv("DTA_PAIR_HANDOFF");
-  p.handoff_commit = ho && strcmp(ho, "commit") == 0 ? 1 : 0;
+  // "commit" = all three hand-offs (P^T, dS^T, R1 free); "commit_p" / "commit_ds" / "commit_r1" = one of them (A/B)
+  p.handoff_commit = !ho ? kDefaultHandoff : strcmp(ho, "commit") == 0 ? 7 : strcmp(ho, "commit_p") == 0 ? 1 : strcmp(ho, "commit_ds") == 0 ? 2
+                     : strcmp(ho, "commit_r1") == 0 ? 4 : strcmp(ho, "commit_p_ds") == 0 ? 3 : strcmp(ho, "arrive") == 0 ? 0 : kDefaultHandoff;
 
   using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                           const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
