@@ -256,11 +256,13 @@ def test_qwen3_0p6b_28_layer_step_vs_fp32_cpu_oracle():
     w_cpu = dict(r["model"].named_parameters())["model.layers.3.mlp.up_proj.weight"]
     w_gpu = dict(model.named_parameters())["model.layers.3.mlp.up_proj.weight"]
     assert torch.equal(w_cpu.detach().bfloat16(), w_gpu.detach().cpu())
-    eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 16384)
-    par = bench.full_model_parity(model, eng, r["model"], r["loss"], r["seqs"])
-    print("full-model parity:", {k: v for k, v in par.items() if k not in ("tolerance", "metric")})
-    assert par["n_params"] == 310                                      # 28 x 11 + 2, the 310 rows of the grad/ artefact
-    assert par["ok"], par
+    for fused_head in (None, True):            # default head policy (kept bf16 logits here), then the fused lm_head (N1)
+        eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 16384)
+        eng.fused_head = fused_head
+        par = bench.full_model_parity(model, eng, r["model"], r["loss"], r["seqs"])
+        print(f"full-model parity (fused_head={fused_head}):", {k: v for k, v in par.items() if k not in ("tolerance", "metric")})
+        assert par["n_params"] == 310                                  # 28 x 11 + 2, the 310 rows of the grad/ artefact
+        assert par["ok"], par
 
 
 def test_qwen3_1p7b_tau2_trie_runs_in_one_pass_with_recompute():
