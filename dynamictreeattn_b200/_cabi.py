@@ -18,7 +18,7 @@ import torch
 _LIB_PATH = Path(os.environ.get("DTA_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libdta_b200.so")
 _lib = None
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 TILE = 128
 
 
@@ -70,6 +70,7 @@ SIGNATURES = {
     "dta_lm_head_stats_splits": (_I, [_L, _L]),
     "dta_lm_head_stats_rows_pad": (_L, [_L]),
     "dta_lm_head_stats": (_I, [_P, _L, _P, _L, _L, _L, _I, _F, _P, _P]),
+    "dta_lm_head_stats_logits": (_I, [_P, _L, _P, _L, _L, _L, _I, _F, _P, _P, _L, _P]),
     "dta_lm_head_dlogits": (_I, [_P, _L, _P, _L, _L, _L, _I, _F, _P, _P, _P, _P, _P, _L, _P]),
     "dta_lm_head_label_logits": (_I, [_P, _L, _P, _L, _I, _L, _P, _P, _L, _F, _P, _P]),
     "dta_rmsnorm_fwd": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P, _P]),
@@ -88,7 +89,7 @@ KERNELS_PER_CALL = {
     "dta_tree_attn_fwd": 1, "dta_tree_attn_bwd": 4,
     "dta_logprob_row_stats": 1, "dta_logprob_gather_labels": 1, "dta_logprob_finalize": 1,
     "dta_logprob_bwd": 1, "dta_logprob_bwd_scatter": 1, "dta_logprob_rowsum_grad": 1,
-    "dta_lm_head_stats": 1, "dta_lm_head_dlogits": 1, "dta_lm_head_label_logits": 1,
+    "dta_lm_head_stats": 1, "dta_lm_head_stats_logits": 1, "dta_lm_head_dlogits": 1, "dta_lm_head_label_logits": 1,
     "dta_rmsnorm_fwd": 1, "dta_rmsnorm_bwd": 1, "dta_qknorm_rope_fwd": 1, "dta_qknorm_rope_bwd": 1,
     "dta_swiglu_fwd": 1, "dta_swiglu_bwd": 1,
 }

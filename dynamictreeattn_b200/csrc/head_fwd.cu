@@ -116,10 +116,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
-// kBackward = false: statistics epilogue (forward).  true: the SAME mainloop recomputes the logits tile and the epilogue
-// writes d loss / d logits = inv_temp * p * (g_H * (-H - log p) - sum g_lp) in bf16 (the one-hot label terms are added
-// by dta_logprob_bwd_scatter), i.e. the recompute GEMM and logprob_bwd_kernel in one pass with no logits in HBM.
-template <bool kBackward>
+// kMode 0: statistics epilogue (forward, no logits anywhere).
+// kMode 1: the SAME mainloop recomputes the logits tile and the epilogue writes d loss / d logits = inv_temp * p *
+//          (g_H * (-H - log p) - sum g_lp) in bf16 (the one-hot label terms are added by dta_logprob_bwd_scatter), i.e.
+//          the recompute GEMM and logprob_bwd_kernel in one pass with no logits in HBM.
+// kMode 2: statistics AND the bf16 logits (into p.dlogits): for a training step that keeps the logits for its backward
+//          -- they are written once, under the MMAs, and not read again in the forward.  The statistics are taken from
+//          the ROUNDED values, so they are exactly the statistics of the tensor the backward will read.
+template <int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 lm_head_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -220,7 +224,7 @@ lm_head_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
     const uint32_t lane_addr = static_cast<uint32_t>(warp << 5) << 16;
     const int64_t row = static_cast<int64_t>(row0) + r;
     const float c = p.inv_temp * kLog2e;
-    if constexpr (kBackward) {
+    if constexpr (kMode == 1) {
       // ================================ epilogue: d loss / d logits, bf16 ===================
       const bool live = row < p.n_rows;
       const float lz2 = live ? p.logz[row] * kLog2e : 0.f;
@@ -290,6 +294,28 @@ lm_head_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
         float x[32];
         tmem_ld_x32(tmem + lane_addr + b * kBN + ch * 32, reinterpret_cast<uint32_t*>(x));
         tmem_ld_wait();
+        if constexpr (kMode == 2) {
+          // keep the logits: round to bf16, store, and continue with the rounded values
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            pk[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+            x[2 * i] = __uint_as_float(pk[i] << 16);
+            x[2 * i + 1] = __uint_as_float(pk[i] & 0xffff0000u);
+          }
+          if (row < p.n_rows) {
+            __nv_bfloat16* dst = p.dlogits + row * p.d_stride + col0 + ch * 32;
+            if (cnt == 32 && (p.d_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.dlogits) & 15) == 0)) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                __stcs(reinterpret_cast<uint4*>(dst) + v, make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < cnt) dst[i] = __float2bfloat16_rn(x[i]);
+            }
+          }
+        }
         float mx = -INFINITY;
         if (cnt == 32) {
 #pragma unroll
@@ -403,17 +429,19 @@ int dta_lm_head_stats_splits(int64_t n_rows, int64_t n_cols) {
 
 int64_t dta_lm_head_stats_rows_pad(int64_t n_rows) { return (n_rows + 2 * head::kBM - 1) / (2 * head::kBM) * (2 * head::kBM); }
 
-static int launch_lm_head(bool backward, const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride,
+static int launch_lm_head(int mode, const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride,
                           int64_t n_rows, int64_t n_cols, int hidden_size, float inv_temperature, float* stats,
                           const float* logz, const float* entropy, const float* g_entropy, const float* g_rowsum,
                           void* dlogits, int64_t d_row_stride, dta_stream_t stream) {
-  DTA_REQUIRE(hidden && weight && (backward ? (logz && entropy && dlogits) : stats != nullptr), "NULL pointer argument");
+  const bool backward = mode == 1;
+  DTA_REQUIRE(hidden && weight && (backward ? (logz && entropy && dlogits) : stats != nullptr) && (mode != 2 || dlogits),
+              "NULL pointer argument");
   DTA_REQUIRE(n_rows >= 1 && n_cols >= 1, "bad shape");
   DTA_REQUIRE(hidden_size >= head::kBK && hidden_size % head::kBK == 0, "hidden size must be a multiple of %d (got %d)",
               head::kBK, hidden_size);
   DTA_REQUIRE(inv_temperature > 0.f, "temperature must be positive");
   DTA_REQUIRE(backward || (reinterpret_cast<uintptr_t>(stats) & 15) == 0, "stats must be 16-byte aligned");
-  DTA_REQUIRE(!backward || d_row_stride >= n_cols, "dlogits row stride shorter than a row");
+  DTA_REQUIRE(mode == 0 || d_row_stride >= n_cols, "logits / dlogits row stride shorter than a row");
   const int n_row_pairs = static_cast<int>((n_rows + 2 * head::kBM - 1) / (2 * head::kBM));
   const int n_tiles = static_cast<int>((n_cols + head::kBN - 1) / head::kBN);
   const int n_split = head::plan_splits(n_row_pairs, n_tiles);
@@ -440,16 +468,20 @@ static int launch_lm_head(bool backward, const void* hidden, int64_t h_row_strid
   static bool configured = false;
   const int smem_bytes = head::Smem::total + 1024;
   if (!configured) {
-    DTA_CHECK_CUDA(cudaFuncSetAttribute(head::lm_head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    DTA_CHECK_CUDA(cudaFuncSetAttribute(head::lm_head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    DTA_CHECK_CUDA(cudaFuncSetAttribute(head::lm_head_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    DTA_CHECK_CUDA(cudaFuncSetAttribute(head::lm_head_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    DTA_CHECK_CUDA(cudaFuncSetAttribute(head::lm_head_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   const ProfileHook hook = take_profile_hook();
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
-  if (backward)
-    head::lm_head_kernel<true><<<2 * n_row_pairs * n_split, head::kThreads, smem_bytes, stream>>>(th, tw, p);
+  const int grid = 2 * n_row_pairs * n_split;
+  if (mode == 1)
+    head::lm_head_kernel<1><<<grid, head::kThreads, smem_bytes, stream>>>(th, tw, p);
+  else if (mode == 2)
+    head::lm_head_kernel<2><<<grid, head::kThreads, smem_bytes, stream>>>(th, tw, p);
   else
-    head::lm_head_kernel<false><<<2 * n_row_pairs * n_split, head::kThreads, smem_bytes, stream>>>(th, tw, p);
+    head::lm_head_kernel<0><<<grid, head::kThreads, smem_bytes, stream>>>(th, tw, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
   return DTA_OK;
@@ -457,15 +489,22 @@ static int launch_lm_head(bool backward, const void* hidden, int64_t h_row_strid
 
 int dta_lm_head_stats(const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride, int64_t n_rows,
                       int64_t n_cols, int hidden_size, float inv_temperature, float* stats, dta_stream_t stream) {
-  return launch_lm_head(false, hidden, h_row_stride, weight, w_row_stride, n_rows, n_cols, hidden_size, inv_temperature, stats,
+  return launch_lm_head(0, hidden, h_row_stride, weight, w_row_stride, n_rows, n_cols, hidden_size, inv_temperature, stats,
                         nullptr, nullptr, nullptr, nullptr, nullptr, 0, stream);
+}
+
+int dta_lm_head_stats_logits(const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride, int64_t n_rows,
+                             int64_t n_cols, int hidden_size, float inv_temperature, float* stats, void* logits,
+                             int64_t l_row_stride, dta_stream_t stream) {
+  return launch_lm_head(2, hidden, h_row_stride, weight, w_row_stride, n_rows, n_cols, hidden_size, inv_temperature, stats,
+                        nullptr, nullptr, nullptr, nullptr, logits, l_row_stride, stream);
 }
 
 int dta_lm_head_dlogits(const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride, int64_t n_rows,
                         int64_t n_cols, int hidden_size, float inv_temperature, const float* logz, const float* entropy,
                         const float* g_entropy, const float* g_lp_rowsum, void* dlogits, int64_t d_row_stride,
                         dta_stream_t stream) {
-  return launch_lm_head(true, hidden, h_row_stride, weight, w_row_stride, n_rows, n_cols, hidden_size, inv_temperature, nullptr,
+  return launch_lm_head(1, hidden, h_row_stride, weight, w_row_stride, n_rows, n_cols, hidden_size, inv_temperature, nullptr,
                         logz, entropy, g_entropy, g_lp_rowsum, dlogits, d_row_stride, stream);
 }
 

@@ -35,8 +35,8 @@ from . import _cabi
 from .attention import use_tree_attention
 from .fused_layers import fused_trunk_forward, supports_fused_trunk
 from .linearize import TrieLayout, linearize_trie
-from .vocab_parallel import (fused_head_supported, lm_head_dlogits_rows, lm_head_logprob_entropy_rows, logprob_entropy_rows,
-                             logprob_entropy_rows_backward)
+from .vocab_parallel import (fused_head_supported, lm_head_dlogits_rows, lm_head_logits_and_stats_rows,
+                             lm_head_logprob_entropy_rows, logprob_entropy_rows, logprob_entropy_rows_backward)
 
 __all__ = ["TreeTrainingEngine", "_get_forkpos"]
 
@@ -223,8 +223,9 @@ class TreeTrainingEngine:
         # True / False force it.  None = by measured cost (profiles/r02/head_bench.log, visit12 in-step A/B): the fused
         # FORWARD beats GEMM + statistics (14.8 vs 21.6 ms at 67k x 151,936) and runs whenever no backward follows
         # (engine.forward); a training step's backward has to recompute the GEMM without kept logits (2.3 ms per
-        # 8192-row chunk fused, against 1.3 ms on kept logits), which makes the fused step 1 % slower and 17 GB
-        # smaller -- so training uses it when the logits would not fit anyway (_can_keep_logits) and keeps them else.
+        # 8192-row chunk fused, against 1.3 ms on kept logits), which makes the no-logits step 1 % slower and 17 GB
+        # smaller -- so training goes logit-free when the logits would not fit anyway (_can_keep_logits); while they
+        # fit, the SAME fused launch also writes them (dta_lm_head_stats_logits) and the backward runs on kept logits.
         env = os.environ.get("DTA_FUSED_HEAD")
         self.fused_head: Optional[bool] = None if env is None else env not in ("0", "")
         self.use_fused_trunk = True      # Qwen3-style bf16 models; others go through the HF attention plugin
@@ -372,12 +373,18 @@ class TreeTrainingEngine:
         ent_nodes = torch.empty(N, dtype=torch.float32, device=dev)
         logz = torch.empty(N, dtype=torch.float32, device=dev)
         kept = [] if keep_logits else None
+        # kept logits come out of the fused lm_head launch (statistics in the GEMM's epilogue, logits written once and
+        # not read back in the forward); a head that is not fusable runs the library GEMM + the row kernel
+        fused_keep = keep_logits and self.fused_head is not False and fused_head_supported(h, W)
         for a in range(0, N, chunk_rows):
             b = min(a + chunk_rows, N)
             e0, e1 = plan.span(a, b)
-            logits = h[a:b] @ W.t()
             row_of = (plan.row[e0:e1] - a).to(torch.int32)
-            x_label, lz, ent = logprob_entropy_rows(logits, plan.label[e0:e1], row_of, 1.0)
+            if fused_keep:
+                logits, x_label, lz, ent = lm_head_logits_and_stats_rows(h[a:b], W, plan.label[e0:e1], row_of, 1.0)
+            else:
+                logits = h[a:b] @ W.t()
+                x_label, lz, ent = logprob_entropy_rows(logits, plan.label[e0:e1], row_of, 1.0)
             lp_nodes[plan.child[e0:e1]] = x_label - lz[row_of.long()]
             ent_nodes[a:b] = ent
             logz[a:b] = lz

@@ -30,7 +30,7 @@ from torch import distributed as dist
 from . import _cabi
 
 __all__ = ["gather_logprobs", "gather_logprobs_entropy", "logprob_entropy_rows", "lm_head_logprob_entropy_rows",
-           "lm_head_dlogits_rows", "fused_head_supported"]
+           "lm_head_dlogits_rows", "lm_head_logits_and_stats_rows", "fused_head_supported"]
 
 _DTYPE_CODE = {torch.bfloat16: 0, torch.float32: 1}
 
@@ -287,6 +287,32 @@ def lm_head_logprob_entropy_rows(hidden: torch.Tensor, weight: torch.Tensor, lab
                                                  row_of.data_ptr() if row_of is not None else None, M, inv_temp,
                                                  x_label.data_ptr(), st))
     return x_label, logz, entropy
+
+
+def lm_head_logits_and_stats_rows(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor,
+                                  row_of: torch.Tensor, inv_temp: float = 1.0):
+    """(logits [R, V] bf16, x_label[M], logz[R], entropy[R]): the fused lm_head launch that ALSO keeps the logits for a
+    backward over them (``logprob_entropy_rows_backward``).  Statistics and label logits are those of the stored bf16
+    tensor -- the same numbers a library GEMM followed by ``logprob_entropy_rows`` gives, without reading the logits
+    back in the forward."""
+    lib = _cabi.load()
+    R, K = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    labels = labels.reshape(-1).to(torch.int64)
+    M = labels.numel()
+    st = _cabi.stream_ptr(dev)
+    with torch.cuda.device(dev):
+        n_split = lib.dta_lm_head_stats_splits(R, V)
+        rows_pad = lib.dta_lm_head_stats_rows_pad(R)
+        stats = torch.empty((n_split, rows_pad, 4), dtype=torch.float32, device=dev)
+        logits = torch.empty((R, V), dtype=torch.bfloat16, device=dev)
+        _cabi.check(lib.dta_lm_head_stats_logits(hidden.data_ptr(), hidden.stride(0), weight.data_ptr(), weight.stride(0), R,
+                                                 V, K, inv_temp, stats.data_ptr(), logits.data_ptr(), logits.stride(0), st))
+        logz, entropy, _ = _k_finalize(stats.view(n_split, rows_pad * 4), R, False)
+        x_label = torch.empty(M, dtype=torch.float32, device=dev)
+        _k_gather_labels(logits, inv_temp, labels, row_of, 0, x_label)      # stored logits are raw: x = logit * inv_temp
+    return logits, x_label, logz, entropy
 
 
 def fused_head_supported(hidden: torch.Tensor, weight: torch.Tensor) -> bool:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTA_ABI_VERSION 5
+#define DTA_ABI_VERSION 6
 #define DTA_TILE 128 /* attention tile edge (queries and keys) */
 
 typedef struct CUstream_st* dta_stream_t;
@@ -220,6 +220,13 @@ int dta_lm_head_stats_splits(int64_t n_rows, int64_t n_cols);
 int64_t dta_lm_head_stats_rows_pad(int64_t n_rows);
 int dta_lm_head_stats(const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride, int64_t n_rows,
                       int64_t n_cols, int hidden_size, float inv_temperature, float* stats, dta_stream_t stream);
+
+/* Same launch that ALSO keeps the logits (bf16, logits[n_rows][l_row_stride]) for a backward that wants them: written
+ * once under the MMAs, never read in the forward; the statistics are those of the ROUNDED values (= of the stored
+ * tensor, as if it had been produced by a library GEMM and reduced by dta_logprob_row_stats). */
+int dta_lm_head_stats_logits(const void* hidden, int64_t h_row_stride, const void* weight, int64_t w_row_stride, int64_t n_rows,
+                             int64_t n_cols, int hidden_size, float inv_temperature, float* stats, void* logits,
+                             int64_t l_row_stride, dta_stream_t stream);
 
 /* Backward of the same fusion: the SAME GEMM mainloop recomputes each logits tile and the epilogue turns it into
  * d loss / d logits (formula of dta_logprob_bwd, without the one-hot label terms: add them with

@@ -86,7 +86,8 @@ def test_device_linearisation_called_and_launches_counted():
     trie = TokenTrie(seqs, [{"w_logprobs": -1.0, "w_entropy": 0.1} for _ in seqs])
     auto.backward(model, trie, tree_oracle.example_loss, block_size=2048)
     delta = {k: _cabi.call_count.get(k, 0) - before.get(k, 0) for k in _cabi.call_count}
-    assert delta["dta_logprob_row_stats"] >= 1 and delta["dta_logprob_bwd"] >= 1 and delta.get("dta_lm_head_stats", 0) == 0
+    assert delta["dta_lm_head_stats_logits"] >= 1 and delta["dta_logprob_bwd"] >= 1                # fused launch keeps the logits
+    assert delta.get("dta_lm_head_stats", 0) == 0 and delta.get("dta_logprob_row_stats", 0) == 0
     before = dict(_cabi.call_count)
     auto.forward(model, TokenTrie(seqs))
     delta = {k: _cabi.call_count.get(k, 0) - before.get(k, 0) for k in _cabi.call_count}
@@ -178,7 +179,7 @@ def test_fused_head_equals_materialised_logits_head():
     attachs = [{"w_logprobs": -1.0, "w_entropy": 0.1} for _ in seqs]
     loss_ref = tree_oracle.dense_backward(ref, seqs, [dict(a) for a in attachs], tree_oracle.example_loss)
     out = {}
-    for fused in (True, False):
+    for fused in (True, False, None):               # no logits at all / library GEMM + row kernels / fused launch that keeps logits
         model.zero_grad(set_to_none=True)
         eng = TreeTrainingEngine(cfg, "cuda", torch.bfloat16, 8192)
         eng.fused_head = fused
@@ -197,6 +198,11 @@ def test_fused_head_equals_materialised_logits_head():
     assert worst < 3e-2, worst
     for a, b in zip(out[True][2], out[False][2]):
         assert (a - b).abs().max().item() < 5e-2
+    # the logits-keeping fused launch reproduces the library-GEMM path: same rounded logits up to the accumulation
+    # order of the two GEMMs
+    assert abs(out[None][0] - out[False][0]) < 1e-3 * abs(loss_ref)
+    worst = max(((out[None][1][n] - g).norm() / (g.norm() + 1e-6)).item() for n, g in out[False][1].items())
+    assert worst < 1e-2, worst
 
 
 def test_layer_recompute_same_gradients_less_memory():

@@ -288,6 +288,28 @@ def test_fused_lm_head_statistics(R, K, V, temp):
     assert (xl1.double() - z_lab).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("R,K,V,temp", [(300, 256, 1003, 1.0), (1100, 1024, 151936, 0.8)])
+def test_fused_lm_head_keeping_logits(R, K, V, temp):
+    """dta_lm_head_stats_logits: the stored bf16 logits equal a bf16 GEMM of the same operands up to accumulation
+    order, and the statistics / label logits are EXACTLY consistent with the stored tensor (they equal what the row
+    kernel computes from it)."""
+    from dynamictreeattn_b200.vocab_parallel import lm_head_logits_and_stats_rows, logprob_entropy_rows
+    g = torch.Generator(device="cuda").manual_seed(R + V + 2)
+    h = torch.randn(R, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(V, K, device="cuda", generator=g) * (3.0 / K ** 0.5)).bfloat16()
+    M = R + 7
+    row_of = torch.randint(0, R, (M,), device="cuda", generator=g).to(torch.int32)
+    labels = torch.randint(0, V, (M,), device="cuda", generator=g)
+    logits, xl, lz, ent = lm_head_logits_and_stats_rows(h, w, labels, row_of, 1.0 / temp)
+    ref = (h.float() @ w.float().t())
+    assert logits.shape == (R, V) and logits.dtype == torch.bfloat16
+    assert ((logits.float() - ref).norm() / ref.norm()).item() < 3e-3            # one bf16 rounding
+    xl2, lz2, ent2 = logprob_entropy_rows(logits, labels, row_of, 1.0 / temp)    # row kernel on the stored tensor
+    assert torch.equal(xl, xl2)
+    # two fp32 reductions of the same values in different orders (per 256-column tile here, per thread stripe there)
+    assert (lz - lz2).abs().max().item() < 3e-5 and (ent - ent2).abs().max().item() < 1e-4
+
+
 @pytest.mark.parametrize("R,K,V,temp", [(300, 256, 1003, 1.0), (700, 1024, 151936, 1.0), (1500, 2048, 18992, 0.7)])
 def test_fused_lm_head_backward(R, K, V, temp):
     """The backward of the fusion (dta_lm_head_dlogits: recompute GEMM + log-prob / entropy backward in the epilogue,
