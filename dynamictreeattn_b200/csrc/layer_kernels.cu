@@ -5,6 +5,7 @@
 // cost more than the attention kernels once attention runs on tcgen05.  All are HBM-bound: bf16 in
 // and out, fp32 math, 16-byte accesses, one pass over each tensor.
 #include "dta_common.cuh"
+#include <cstdlib>
 #include "../../include/dta_b200.h"
 #include <cuda_bf16.h>
 
@@ -390,7 +391,9 @@ __global__ void __launch_bounds__(256) qknorm_rope_bwd_kernel(const QkBwdArgs a)
 // ------------------------------------------------------------------------------------
 static constexpr int kQkUnroll = 4;   // head PAIRS in flight per warp
 
-__global__ void __launch_bounds__(256) qknorm_rope_fwd_v8_kernel(const QkArgs a) {
+// kMinBlocks: resident blocks per SM the register allocation must allow (occupancy vs registers: A/B knob DTA_QK_OCC)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) qknorm_rope_fwd_v8_kernel(const QkArgs a) {
   const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   const int heads = a.hq + a.hkv;
   float wq[8], wk[8];
@@ -448,7 +451,8 @@ __global__ void __launch_bounds__(256) qknorm_rope_fwd_v8_kernel(const QkArgs a)
   }
 }
 
-__global__ void __launch_bounds__(256) qknorm_rope_bwd_v8_kernel(const QkBwdArgs a) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) qknorm_rope_bwd_v8_kernel(const QkBwdArgs a) {
   const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   const int heads = a.hq + a.hkv;
   float wq[8], wk[8], accq[8], acck[8];
@@ -580,6 +584,16 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace dta
 
+namespace dta {
+// measured at the bench shape (tools/layer_bench.py, round 2): forward 0.230 / 0.206 / 0.224 ms at 2 / 3 / 4 blocks per SM
+// (80 registers at 3: the loads of more warps in flight win over 12 bytes of spills); backward 0.299 / 0.398 / 0.494 (spills)
+static constexpr int kDefaultQkFwdOcc = 3, kDefaultQkBwdOcc = 2;
+static int qk_occupancy(int dflt) {
+  const char* e = getenv("DTA_QK_OCC");
+  return e ? atoi(e) : dflt;
+}
+}  // namespace dta
+
 using namespace dta;
 
 extern "C" {
@@ -652,9 +666,12 @@ int dta_qknorm_rope_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stri
   const bool v8 = q_row_stride % 8 == 0 && q_head_stride % 8 == 0 && k_row_stride % 8 == 0 && k_head_stride % 8 == 0 &&
                   aligned16(q) && aligned16(k) && aligned16(q_out) && aligned16(k_out) && aligned16(wq) && aligned16(wk) &&
                   aligned16(cos_sin);
-  if (v8)
-    qknorm_rope_fwd_v8_kernel<<<elem_grid(n_rows * 32, 256), 256, 0, stream>>>(a);
-  else
+  if (v8) {
+    const int occ = qk_occupancy(kDefaultQkFwdOcc);
+    if (occ >= 4) qknorm_rope_fwd_v8_kernel<4><<<elem_grid(n_rows * 32, 256), 256, 0, stream>>>(a);
+    else if (occ == 3) qknorm_rope_fwd_v8_kernel<3><<<elem_grid(n_rows * 32, 256), 256, 0, stream>>>(a);
+    else qknorm_rope_fwd_v8_kernel<2><<<elem_grid(n_rows * 32, 256), 256, 0, stream>>>(a);
+  } else
     qknorm_rope_fwd_kernel<<<elem_grid(n_rows * (n_q_heads + n_kv_heads) * 32, 256), 256, 0, stream>>>(a);
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
@@ -684,9 +701,12 @@ int dta_qknorm_rope_bwd(const void* dq_out, const void* dk_out, const void* q, i
   const int64_t cap = 8 * static_cast<int64_t>(sm_count());
   int64_t grid = ((v8 ? n_rows : n_rows * (n_q_heads + n_kv_heads)) * 32 + 255) / 256;
   if (grid > cap) grid = cap;
-  if (v8)
-    qknorm_rope_bwd_v8_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(a);
-  else
+  if (v8) {
+    const int occ = qk_occupancy(kDefaultQkBwdOcc);
+    if (occ >= 4) qknorm_rope_bwd_v8_kernel<4><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+    else if (occ == 3) qknorm_rope_bwd_v8_kernel<3><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+    else qknorm_rope_bwd_v8_kernel<2><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  } else
     qknorm_rope_bwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(a);
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;

@@ -307,7 +307,7 @@ def test_fused_lm_head_keeping_logits(R, K, V, temp):
     xl2, lz2, ent2 = logprob_entropy_rows(logits, labels, row_of, 1.0 / temp)    # row kernel on the stored tensor
     assert torch.equal(xl, xl2)
     # two fp32 reductions of the same values in different orders (per 256-column tile here, per thread stripe there)
-    assert (lz - lz2).abs().max().item() < 3e-5 and (ent - ent2).abs().max().item() < 1e-4
+    assert (lz - lz2).abs().max().item() < 3e-5 and (ent - ent2).abs().max().item() < 5e-4
 
 
 @pytest.mark.parametrize("R,K,V,temp", [(300, 256, 1003, 1.0), (700, 1024, 151936, 1.0), (1500, 2048, 18992, 0.7)])
