@@ -93,3 +93,25 @@ def test_stale_library_is_refused(monkeypatch):
     monkeypatch.undo()
     _cabi._lib = None
     assert _cabi.load(build_if_missing=False) is not None
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/dta_b200.h is the boundary a non-Python host binds: it must compile as strict C99 (no C++ or torch
+    types in any signature) and a C program must link against the in-tree library and read its ABI version."""
+    import shutil
+    import subprocess
+    from dynamictreeattn_b200 import _cabi
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    _cabi.load()
+    src = tmp_path / "abi_test.c"
+    src.write_text('#include "dta_b200.h"\n'
+                   'int main(void) { return dta_abi_version() == DTA_ABI_VERSION ? 0 : 1; }\n')
+    exe = tmp_path / "abi_test"
+    lib_dir = _cabi.lib_path().parent
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"), str(src),
+                        "-o", str(exe), "-L", str(lib_dir), "-ldta_b200", f"-Wl,-rpath,{lib_dir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
