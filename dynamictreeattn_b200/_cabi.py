@@ -18,7 +18,7 @@ import torch
 _LIB_PATH = Path(os.environ.get("DTA_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libdta_b200.so")
 _lib = None
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 TILE = 128
 
 
@@ -61,6 +61,7 @@ SIGNATURES = {
     "dta_profile_next_attn": (_I, [_P, _P]),
     "dta_tree_attn_bwd_workspace_bytes": (_Z, [C.POINTER(AttnShape)]),
     "dta_tree_attn_bwd": (_I, [_P] * 9 + [C.POINTER(AttnMeta), C.POINTER(AttnShape), _P, _P]),
+    "dta_tree_attn_bwd_f32dq": (_I, [_P] * 9 + [C.POINTER(AttnMeta), C.POINTER(AttnShape), _P, _P]),
     "dta_logprob_row_stats": (_I, [_P, _I, _L, _L, _L, _F, _P, _L, _P, _P]),
     "dta_logprob_gather_labels": (_I, [_P, _I, _L, _L, _F, _P, _P, _L, _L, _P, _L, _P]),
     "dta_logprob_finalize": (_I, [_P, _I, _L, _L, _P, _P, _P, _P]),
@@ -78,6 +79,8 @@ SIGNATURES = {
     "dta_qknorm_rope_fwd": (_I, [_P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P, _P, _P, _P]),
     "dta_qknorm_rope_bwd": (_I, [_P, _P, _P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _L, _I, _I, _I,
                                  _P, _L, _L, _P, _L, _L, _P, _P, _P]),
+    "dta_qknorm_rope_bwd_f32dq": (_I, [_P, _P, _P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _L, _I, _I, _I,
+                                       _P, _L, _L, _P, _L, _L, _P, _P, _P]),
     "dta_swiglu_fwd": (_I, [_P, _P, _L, _P, _P]),
     "dta_swiglu_bwd": (_I, [_P, _P, _P, _L, _P, _P, _P]),
 }
@@ -86,11 +89,11 @@ SIGNATURES = {
 # kernels launched per successful call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
     "dta_lcp_adjacent": 1, "dta_trie_linearize": 2, "dta_trie_paths": 1, "dta_tile_meta": 2, "dta_trie_build": 3,
-    "dta_tree_attn_fwd": 1, "dta_tree_attn_bwd": 4,
+    "dta_tree_attn_fwd": 1, "dta_tree_attn_bwd": 4, "dta_tree_attn_bwd_f32dq": 4,
     "dta_logprob_row_stats": 1, "dta_logprob_gather_labels": 1, "dta_logprob_finalize": 1,
     "dta_logprob_bwd": 1, "dta_logprob_bwd_scatter": 1, "dta_logprob_rowsum_grad": 1,
     "dta_lm_head_stats": 1, "dta_lm_head_stats_logits": 1, "dta_lm_head_dlogits": 1, "dta_lm_head_label_logits": 1,
-    "dta_rmsnorm_fwd": 1, "dta_rmsnorm_bwd": 1, "dta_qknorm_rope_fwd": 1, "dta_qknorm_rope_bwd": 1,
+    "dta_rmsnorm_fwd": 1, "dta_rmsnorm_bwd": 1, "dta_qknorm_rope_fwd": 1, "dta_qknorm_rope_bwd": 1, "dta_qknorm_rope_bwd_f32dq": 1,
     "dta_swiglu_fwd": 1, "dta_swiglu_bwd": 1,
 }
 launch_count = 0          # kernels of OURS launched by this process so far

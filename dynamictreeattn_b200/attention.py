@@ -87,24 +87,30 @@ def tree_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, la
     return q, k, v, out, lse
 
 
-def tree_attention_backward(q, k, v, out, lse, dout, layout: TrieLayout, scale: float):
-    """Kernel call, no autograd: (dq, dk, dv) bf16 with the shapes of q, k, v."""
+def tree_attention_backward(q, k, v, out, lse, dout, layout: TrieLayout, scale: float, dq_fp32: bool = False):
+    """Kernel call, no autograd: (dq, dk, dv) with the shapes of q, k, v; dk / dv bf16; dq bf16, or — ``dq_fp32`` —
+    the kernel's own fp32 accumulator [n_pad, Hq, D] handed back without the conversion pass (its consumer, the
+    q/k-norm + RoPE backward, reads it directly)."""
     lib = _cabi.load()
     dout = dout.contiguous()
-    dq = torch.empty((q.shape[0], q.shape[1], q.shape[2]), dtype=q.dtype, device=q.device)
     dk = torch.empty((k.shape[0], k.shape[1], k.shape[2]), dtype=k.dtype, device=k.device)
     dv = torch.empty_like(dk)
-    # the kernel addresses dq/dk/dv with the q/k/v strides: give it same-stride views
-    shape = _shape(layout, dq, dk, dv, out, scale)
-    if (q.stride() != dq.stride()) or (k.stride() != dk.stride()) or (v.stride() != dv.stride()):
-        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    if dq_fp32:
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()       # the kernel addresses dk / dv with the k / v strides
+        dq = torch.empty((layout.n_pad, q.shape[1], q.shape[2]), dtype=torch.float32, device=q.device)
+        shape = _shape(layout, q, dk, dv, out, scale)
+    else:
+        dq = torch.empty((q.shape[0], q.shape[1], q.shape[2]), dtype=q.dtype, device=q.device)
+        # the kernel addresses dq/dk/dv with the q/k/v strides: give it same-stride views
+        shape = _shape(layout, dq, dk, dv, out, scale)
+        if (q.stride() != dq.stride()) or (k.stride() != dk.stride()) or (v.stride() != dv.stride()):
+            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
     ws = torch.empty(lib.dta_tree_attn_bwd_workspace_bytes(C.byref(shape)), dtype=torch.uint8, device=q.device)
     meta = layout.meta()
     _arm_profile(lib, "bwd")
-    _cabi.check(lib.dta_tree_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
-                                      dout.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
-                                      dv.data_ptr(), C.byref(meta), C.byref(shape), ws.data_ptr(),
-                                      _cabi.stream_ptr(q.device)))
+    fn = lib.dta_tree_attn_bwd_f32dq if dq_fp32 else lib.dta_tree_attn_bwd
+    _cabi.check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dq.data_ptr(),
+                   dk.data_ptr(), dv.data_ptr(), C.byref(meta), C.byref(shape), ws.data_ptr(), _cabi.stream_ptr(q.device)))
     return dq, dk, dv
 
 

@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 
 // dq (bf16, q strides) <- dq_accum (fp32 [n_pad, Hq, 128])
 // + for key tiles whose query range was split: dk / dv (bf16, k / v strides) <- the fp32 partial-sum accumulators
-__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, int n_nodes, int n_heads,
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, int n_nodes, int n_dq_rows, int n_heads,
                                                               int64_t row_stride, int64_t head_stride,
                                                               __nv_bfloat16* __restrict__ dq,
                                                               const int32_t* __restrict__ split_list,
@@ -854,7 +854,8 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
       }
     }
   }
-  const int64_t n_vec = static_cast<int64_t>(n_nodes) * n_heads * (kT / 8);
+  // n_dq_rows = n_nodes, or 0 when the caller keeps dQ in fp32 (only the split tiles' dK / dV are converted then)
+  const int64_t n_vec = static_cast<int64_t>(n_dq_rows) * n_heads * (kT / 8);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_vec;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % (kT / 8)) * 8;
@@ -937,10 +938,14 @@ size_t dta_tree_attn_bwd_workspace_bytes(const dta_attn_shape_t* sh) {
   return bwd_workspace_layout(sh, sm_count()).total;
 }
 
-int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
-                      const float* lse, void* dq, void* dk, void* dv, const dta_attn_meta_t* meta,
-                      const dta_attn_shape_t* sh, void* workspace, dta_stream_t stream) {
-  DTA_REQUIRE(q && k && v && out && dout && lse && dq && dk && dv && meta && sh && workspace, "NULL pointer argument");
+}  // extern "C" (debug entry points, workspace size)
+
+// dq_f32 != NULL: that buffer ([n_pad, Hq, 128] fp32, 16-byte aligned) IS the dQ accumulator and is left as the result; the
+// bf16 dq tensor is not written (dq may be NULL) -- the consumer (dta_qknorm_rope_bwd_f32dq) reads the fp32 values.
+static int tree_attn_bwd_impl(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                              const float* lse, void* dq, float* dq_f32, void* dk, void* dv, const dta_attn_meta_t* meta,
+                              const dta_attn_shape_t* sh, void* workspace, dta_stream_t stream) {
+  DTA_REQUIRE(q && k && v && out && dout && lse && (dq || dq_f32) && dk && dv && meta && sh && workspace, "NULL pointer argument");
   DTA_REQUIRE(sh->head_dim == kT, "head_dim must be %d (got %d)", kT, sh->head_dim);
   DTA_REQUIRE(sh->n_nodes >= 1 && sh->n_pad % DTA_TILE == 0 && sh->n_pad >= sh->n_nodes &&
                   sh->n_pad - sh->n_nodes < DTA_TILE,
@@ -949,7 +954,7 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   DTA_REQUIRE(meta->subtree_end && meta->kmin_end && meta->k_order && meta->k_qlast, "NULL metadata pointer");
   DTA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   DTA_REQUIRE((reinterpret_cast<uintptr_t>(lse) & 15) == 0, "lse must be 16-byte aligned");
-  const uintptr_t align_or = reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
+  const uintptr_t align_or = reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dq_f32) | reinterpret_cast<uintptr_t>(dk) |
                              reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(out) |
                              reinterpret_cast<uintptr_t>(dout);
   DTA_REQUIRE((align_or & 15) == 0, "tensors must be 16-byte aligned");
@@ -960,7 +965,7 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
 
   const BwdWorkspace wl = bwd_workspace_layout(sh, sm_count());
   uint8_t* ws8 = static_cast<uint8_t*>(workspace);
-  float* dq_accum = reinterpret_cast<float*>(ws8 + wl.dq);
+  float* dq_accum = dq_f32 ? dq_f32 : reinterpret_cast<float*>(ws8 + wl.dq);
   const size_t dq_bytes = static_cast<size_t>(sh->n_pad) * sh->n_q_heads * kT * sizeof(float);
   uint4* aug_lse = reinterpret_cast<uint4*>(ws8 + wl.aug_lse);
   uint4* aug_delta = reinterpret_cast<uint4*>(ws8 + wl.aug_delta);
@@ -1074,17 +1079,34 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
   }
 
   {
-    const int64_t n_vec = static_cast<int64_t>(sh->n_nodes) * sh->n_q_heads * (kT / 8);
+    // (fp32 dq requested: only the split key tiles' dk / dv are converted; n_nodes = 0 empties the dq loop)
+    const int64_t n_vec = dq_f32 ? 1 : static_cast<int64_t>(sh->n_nodes) * sh->n_q_heads * (kT / 8);
     int64_t grid = (n_vec + 255) / 256;
     const int64_t cap = 16 * static_cast<int64_t>(sm_count());
     if (grid > cap) grid = cap;
-    attn_dq_convert_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
-        dq_accum, sh->n_nodes, sh->n_q_heads, sh->q_row_stride, sh->q_head_stride, static_cast<__nv_bfloat16*>(dq),
+    attn_dq_convert_kernel<<<static_cast<int>(dq_f32 ? 4 * sm_count() : grid), 256, 0, stream>>>(
+        dq_accum, sh->n_nodes, dq_f32 ? 0 : sh->n_nodes, sh->n_q_heads, sh->q_row_stride, sh->q_head_stride, static_cast<__nv_bfloat16*>(dq),
         split_list, n_work + 1, sh->n_kv_heads, dk_acc, dv_acc, sh->k_row_stride, sh->k_head_stride, sh->v_row_stride,
         sh->v_head_stride, static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv));
     DTA_CHECK_CUDA(cudaGetLastError());
   }
   return DTA_OK;
+}
+
+extern "C" {
+
+int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                      const float* lse, void* dq, void* dk, void* dv, const dta_attn_meta_t* meta,
+                      const dta_attn_shape_t* sh, void* workspace, dta_stream_t stream) {
+  DTA_REQUIRE(dq != nullptr, "NULL pointer argument");
+  return tree_attn_bwd_impl(q, k, v, out, dout, lse, dq, nullptr, dk, dv, meta, sh, workspace, stream);
+}
+
+int dta_tree_attn_bwd_f32dq(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                            const float* lse, float* dq_f32, void* dk, void* dv, const dta_attn_meta_t* meta,
+                            const dta_attn_shape_t* sh, void* workspace, dta_stream_t stream) {
+  DTA_REQUIRE(dq_f32 != nullptr, "NULL pointer argument");
+  return tree_attn_bwd_impl(q, k, v, out, dout, lse, nullptr, dq_f32, dk, dv, meta, sh, workspace, stream);
 }
 
 }  // extern "C"

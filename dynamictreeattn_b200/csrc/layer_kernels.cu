@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(256) qknorm_rope_fwd_kernel(const QkArgs a) {
 
 struct QkBwdArgs {
   const __nv_bfloat16* dq_out; const __nv_bfloat16* dk_out;   // contiguous [N, H, 128]
+  const float* dq_out_f32;                                    // kDqF32: the attention backward's fp32 dQ accumulator, read directly
   const __nv_bfloat16* q; int64_t q_row, q_head;              // raw projections
   const __nv_bfloat16* k; int64_t k_row, k_head;
   __nv_bfloat16* dq; int64_t dq_row, dq_head;                 // gradients of the raw projections
@@ -451,7 +452,9 @@ __global__ void __launch_bounds__(256, kMinBlocks) qknorm_rope_fwd_v8_kernel(con
   }
 }
 
-template <int kMinBlocks>
+// kDqF32: d q_out comes as the fp32 accumulator of the attention backward ([N, Hq, 128] contiguous): the bf16 dq tensor and
+// the kernel that used to write it (attn_dq_convert) drop out of the step
+template <int kMinBlocks, bool kDqF32, int kUnroll>
 __global__ void __launch_bounds__(256, kMinBlocks) qknorm_rope_bwd_v8_kernel(const QkBwdArgs a) {
   const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   const int heads = a.hq + a.hkv;
@@ -472,29 +475,42 @@ __global__ void __launch_bounds__(256, kMinBlocks) qknorm_rope_bwd_v8_kernel(con
 #pragma unroll
       for (int j = 0; j < 8; ++j) sn[j] = -sn[j];          // transpose of the rotation: second half gets - do[i] s
     }
-    for (int h0 = 0; h0 < heads; h0 += 2 * kQkUnroll) {
-      uint4 graw[kQkUnroll], xraw[kQkUnroll];
-      float rstd_u[kQkUnroll];
+    for (int h0 = 0; h0 < heads; h0 += 2 * kUnroll) {
+      uint4 graw[kUnroll], xraw[kUnroll];
+      float4 gf[kDqF32 ? kUnroll : 1][2];
+      float rstd_u[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kQkUnroll; ++u) {
+      for (int u = 0; u < kUnroll; ++u) {
         const int h = h0 + 2 * u + half;
         graw[u] = xraw[u] = make_uint4(0, 0, 0, 0);
         rstd_u[u] = 0.f;
         if (h < heads) {
           const bool is_q = h < a.hq;
           const int hh = is_q ? h : h - a.hq;
-          graw[u] = ldg16((is_q ? a.dq_out + (n * a.hq + hh) * 128 : a.dk_out + (n * a.hkv + hh) * 128) + hl * 8);
+          if (kDqF32 && is_q) {
+            const float4* src = reinterpret_cast<const float4*>(a.dq_out_f32 + (n * a.hq + hh) * 128 + hl * 8);
+            gf[kDqF32 ? u : 0][0] = __ldg(src);
+            gf[kDqF32 ? u : 0][1] = __ldg(src + 1);
+          } else {
+            graw[u] = ldg16((is_q ? a.dq_out + (n * a.hq + hh) * 128 : a.dk_out + (n * a.hkv + hh) * 128) + hl * 8);
+          }
           xraw[u] = ldg16((is_q ? a.q + n * a.q_row + hh * a.q_head : a.k + n * a.k_row + hh * a.k_head) + hl * 8);
           rstd_u[u] = __ldg(a.rstd + n * heads + h);
         }
       }
 #pragma unroll
-      for (int u = 0; u < kQkUnroll; ++u) {
+      for (int u = 0; u < kUnroll; ++u) {
         const int h = h0 + 2 * u + half;
         const bool is_q = h < a.hq;
         const int hh = is_q ? h : h - a.hq;
         float go[8], xh[8], g[8];
-        cvt8(graw[u], go);
+        if (kDqF32 && is_q) {
+          const float4 g0 = gf[kDqF32 ? u : 0][0], g1 = gf[kDqF32 ? u : 0][1];
+          go[0] = g0.x; go[1] = g0.y; go[2] = g0.z; go[3] = g0.w;
+          go[4] = g1.x; go[5] = g1.y; go[6] = g1.z; go[7] = g1.w;
+        } else {
+          cvt8(graw[u], go);
+        }
         cvt8(xraw[u], xh);
         const float rstd = rstd_u[u];
         float dot = 0.f;
@@ -677,17 +693,17 @@ int dta_qknorm_rope_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stri
   return DTA_OK;
 }
 
-int dta_qknorm_rope_bwd(const void* dq_out, const void* dk_out, const void* q, int64_t q_row_stride,
-                        int64_t q_head_stride, const void* k, int64_t k_row_stride, int64_t k_head_stride,
-                        const void* wq, const void* wk, const int32_t* depth, const float* cos_sin, const float* rstd,
-                        int64_t n_rows, int n_q_heads, int n_kv_heads, int head_dim, void* dq, int64_t dq_row_stride,
-                        int64_t dq_head_stride, void* dk, int64_t dk_row_stride, int64_t dk_head_stride, float* dwq,
-                        float* dwk, dta_stream_t stream) {
+static int launch_qknorm_rope_bwd(const void* dq_out, const float* dq_out_f32, const void* dk_out, const void* q,
+                                  int64_t q_row_stride, int64_t q_head_stride, const void* k, int64_t k_row_stride,
+                                  int64_t k_head_stride, const void* wq, const void* wk, const int32_t* depth,
+                                  const float* cos_sin, const float* rstd, int64_t n_rows, int n_q_heads, int n_kv_heads,
+                                  int head_dim, void* dq, int64_t dq_row_stride, int64_t dq_head_stride, void* dk,
+                                  int64_t dk_row_stride, int64_t dk_head_stride, float* dwq, float* dwk, dta_stream_t stream) {
   DTA_REQUIRE(head_dim == 128, "head_dim must be 128 (got %d)", head_dim);
   if (n_rows == 0) return DTA_OK;
-  DTA_REQUIRE(dq_out && dk_out && q && k && wq && wk && depth && cos_sin && rstd && dq && dk && dwq && dwk,
+  DTA_REQUIRE((dq_out || dq_out_f32) && dk_out && q && k && wq && wk && depth && cos_sin && rstd && dq && dk && dwq && dwk,
               "NULL pointer argument");
-  QkBwdArgs a{static_cast<const __nv_bfloat16*>(dq_out), static_cast<const __nv_bfloat16*>(dk_out),
+  QkBwdArgs a{static_cast<const __nv_bfloat16*>(dq_out), static_cast<const __nv_bfloat16*>(dk_out), dq_out_f32,
               static_cast<const __nv_bfloat16*>(q), q_row_stride, q_head_stride,
               static_cast<const __nv_bfloat16*>(k), k_row_stride, k_head_stride,
               static_cast<__nv_bfloat16*>(dq), dq_row_stride, dq_head_stride,
@@ -696,20 +712,47 @@ int dta_qknorm_rope_bwd(const void* dq_out, const void* dk_out, const void* q, i
               dwq, dwk, n_rows, n_q_heads, n_kv_heads};
   const bool v8 = q_row_stride % 8 == 0 && q_head_stride % 8 == 0 && k_row_stride % 8 == 0 && k_head_stride % 8 == 0 &&
                   dq_row_stride % 8 == 0 && dq_head_stride % 8 == 0 && dk_row_stride % 8 == 0 && dk_head_stride % 8 == 0 &&
-                  aligned16(q) && aligned16(k) && aligned16(dq) && aligned16(dk) && aligned16(dq_out) && aligned16(dk_out) &&
-                  aligned16(wq) && aligned16(wk) && aligned16(cos_sin);
+                  aligned16(q) && aligned16(k) && aligned16(dq) && aligned16(dk) && (dq_out_f32 ? aligned16(dq_out_f32) : aligned16(dq_out)) &&
+                  aligned16(dk_out) && aligned16(wq) && aligned16(wk) && aligned16(cos_sin);
+  DTA_REQUIRE(v8 || !dq_out_f32, "the fp32-dq variant needs 16-byte aligned tensors and strides that are multiples of 8");
   const int64_t cap = 8 * static_cast<int64_t>(sm_count());
   int64_t grid = ((v8 ? n_rows : n_rows * (n_q_heads + n_kv_heads)) * 32 + 255) / 256;
   if (grid > cap) grid = cap;
-  if (v8) {
+  if (v8 && dq_out_f32) {
+    qknorm_rope_bwd_v8_kernel<2, true, 2><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  } else if (v8) {
     const int occ = qk_occupancy(kDefaultQkBwdOcc);
-    if (occ >= 4) qknorm_rope_bwd_v8_kernel<4><<<static_cast<int>(grid), 256, 0, stream>>>(a);
-    else if (occ == 3) qknorm_rope_bwd_v8_kernel<3><<<static_cast<int>(grid), 256, 0, stream>>>(a);
-    else qknorm_rope_bwd_v8_kernel<2><<<static_cast<int>(grid), 256, 0, stream>>>(a);
-  } else
+    if (occ >= 4) qknorm_rope_bwd_v8_kernel<4, false, kQkUnroll><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+    else if (occ == 3) qknorm_rope_bwd_v8_kernel<3, false, kQkUnroll><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+    else qknorm_rope_bwd_v8_kernel<2, false, kQkUnroll><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  } else {
     qknorm_rope_bwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  }
   DTA_CHECK_CUDA(cudaGetLastError());
   return DTA_OK;
+}
+
+int dta_qknorm_rope_bwd(const void* dq_out, const void* dk_out, const void* q, int64_t q_row_stride,
+                        int64_t q_head_stride, const void* k, int64_t k_row_stride, int64_t k_head_stride,
+                        const void* wq, const void* wk, const int32_t* depth, const float* cos_sin, const float* rstd,
+                        int64_t n_rows, int n_q_heads, int n_kv_heads, int head_dim, void* dq, int64_t dq_row_stride,
+                        int64_t dq_head_stride, void* dk, int64_t dk_row_stride, int64_t dk_head_stride, float* dwq,
+                        float* dwk, dta_stream_t stream) {
+  return launch_qknorm_rope_bwd(dq_out, nullptr, dk_out, q, q_row_stride, q_head_stride, k, k_row_stride, k_head_stride, wq, wk,
+                                depth, cos_sin, rstd, n_rows, n_q_heads, n_kv_heads, head_dim, dq, dq_row_stride, dq_head_stride,
+                                dk, dk_row_stride, dk_head_stride, dwq, dwk, stream);
+}
+
+int dta_qknorm_rope_bwd_f32dq(const float* dq_out_f32, const void* dk_out, const void* q, int64_t q_row_stride,
+                              int64_t q_head_stride, const void* k, int64_t k_row_stride, int64_t k_head_stride,
+                              const void* wq, const void* wk, const int32_t* depth, const float* cos_sin, const float* rstd,
+                              int64_t n_rows, int n_q_heads, int n_kv_heads, int head_dim, void* dq, int64_t dq_row_stride,
+                              int64_t dq_head_stride, void* dk, int64_t dk_row_stride, int64_t dk_head_stride, float* dwq,
+                              float* dwk, dta_stream_t stream) {
+  DTA_REQUIRE(dq_out_f32 != nullptr, "NULL fp32 dq");
+  return launch_qknorm_rope_bwd(nullptr, dq_out_f32, dk_out, q, q_row_stride, q_head_stride, k, k_row_stride, k_head_stride, wq,
+                                wk, depth, cos_sin, rstd, n_rows, n_q_heads, n_kv_heads, head_dim, dq, dq_row_stride,
+                                dq_head_stride, dk, dk_row_stride, dk_head_stride, dwq, dwk, stream);
 }
 
 int dta_swiglu_fwd(const void* gate, const void* up, int64_t n_elems, void* out, dta_stream_t stream) {

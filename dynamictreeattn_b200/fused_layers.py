@@ -10,6 +10,7 @@ non-default RoPE, head_dim != 128, sliding-window layers) take the generic HF-pl
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -110,6 +111,70 @@ class _QKNormRope(torch.autograd.Function):
         return dq, dk, dwq.to(wq.dtype), dwk.to(wk.dtype), None, None, None
 
 
+class _QKNormRopeAttention(torch.autograd.Function):
+    """q/k-norm + RoPE followed by tree attention as ONE autograd node (they are adjacent in the model,
+    HF models/qwen3/modeling_qwen3.py:263-287).  Same kernels in the forward; in the backward the attention kernel's
+    fp32 dQ accumulator goes straight into the q/k-norm + RoPE backward (``dta_tree_attn_bwd_f32dq`` ->
+    ``dta_qknorm_rope_bwd_f32dq``): the bf16 dq tensor, its conversion kernel and one rounding disappear.
+    ``kept = (out, lse)``: a recomputed layer hands back what its first pass kept and the attention forward is skipped."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, wq, wk, depth, table, eps: float, layout, scaling: float, kept):
+        from .attention import tree_attention_forward
+        lib = _cabi.load()
+        n, hq, d = q.shape
+        hkv = k.shape[1]
+        q_rot = torch.empty((n, hq, d), dtype=q.dtype, device=q.device)
+        k_rot = torch.empty((n, hkv, d), dtype=k.dtype, device=k.device)
+        rstd = torch.empty((n, hq + hkv), dtype=torch.float32, device=q.device)
+        _cabi.check(lib.dta_qknorm_rope_fwd(q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0),
+                                            k.stride(1), wq.data_ptr(), wk.data_ptr(), depth.data_ptr(),
+                                            table.data_ptr(), n, hq, hkv, d, eps, q_rot.data_ptr(),
+                                            k_rot.data_ptr(), rstd.data_ptr(), _st(q)))
+        if kept is None:
+            _, _, vv, out, lse = tree_attention_forward(q_rot, k_rot, v, layout, scaling)
+        else:
+            from .attention import _kernel_ready
+            out, lse = kept
+            vv = _kernel_ready(v)
+        ctx.save_for_backward(q, k, wq, wk, depth, table, rstd, q_rot, k_rot, vv, out, lse)
+        ctx.layout, ctx.scaling = layout, scaling
+        return out.view(out.shape) if kept is not None else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .attention import tree_attention_backward
+        lib = _cabi.load()
+        q, k, wq, wk, depth, table, rstd, q_rot, k_rot, v, out, lse = ctx.saved_tensors
+        n, hq, d = q.shape
+        hkv = k.shape[1]
+        dq32, dk_rot, dv = tree_attention_backward(q_rot, k_rot, v, out, lse, dout, ctx.layout, ctx.scaling, dq_fp32=True)
+        dq = torch.empty((n, hq, d), dtype=q.dtype, device=q.device)
+        dk = torch.empty((n, hkv, d), dtype=k.dtype, device=k.device)
+        dwq = torch.zeros(d, dtype=torch.float32, device=q.device)
+        dwk = torch.zeros(d, dtype=torch.float32, device=q.device)
+        _cabi.check(lib.dta_qknorm_rope_bwd_f32dq(dq32.data_ptr(), dk_rot.data_ptr(), q.data_ptr(), q.stride(0), q.stride(1),
+                                                  k.data_ptr(), k.stride(0), k.stride(1), wq.data_ptr(), wk.data_ptr(),
+                                                  depth.data_ptr(), table.data_ptr(), rstd.data_ptr(), n, hq, hkv, d,
+                                                  dq.data_ptr(), dq.stride(0), dq.stride(1), dk.data_ptr(), dk.stride(0),
+                                                  dk.stride(1), dwq.data_ptr(), dwk.data_ptr(), _st(q)))
+        return dq, dk, dv, dwq.to(wq.dtype), dwk.to(wk.dtype), None, None, None, None, None, None
+
+
+def qknorm_rope_attention(q, k, v, wq, wk, depth, table, eps: float, layout, scaling: float, kept=None):
+    """tree_attention(qknorm_rope(q, k), v) with the fused backward; ``kept``: see ``_QKNormRopeAttention``."""
+    return _QKNormRopeAttention.apply(q, k, v, wq, wk, depth, table, eps, layout, scaling, kept)
+
+
+def _qk_fusable(q, k, v) -> bool:
+    """The fp32-dq backward needs 16-byte aligned views with strides that are multiples of 8 elements."""
+    ok = lambda t: t.stride(2) == 1 and t.stride(0) % 8 == 0 and t.stride(1) % 8 == 0 and t.data_ptr() % 16 == 0   # noqa: E731
+    return FUSE_QK_ATTENTION and ok(q) and ok(k) and ok(v)
+
+
+FUSE_QK_ATTENTION = os.environ.get("DTA_FUSE_QK_ATTN", "1") not in ("0", "")
+
+
 def qknorm_rope(q, k, wq, wk, depth, table, eps: float):
     """q [N,Hq,128], k [N,Hkv,128] (strided views ok) -> per-head RMSNorm * w, then RoPE at ``depth``."""
     return _QKNormRope.apply(q, k, wq, wk, depth, table, eps)
@@ -206,15 +271,19 @@ def supports_fused_trunk(model) -> bool:
     return p.is_cuda and p.dtype == torch.bfloat16
 
 
-def _layer_forward(layer, x, residual, n, hq, hkv, d, depth, table, eps, attn_fn):
+def _layer_forward(layer, x, residual, n, hq, hkv, d, depth, table, eps, attn_fn, qk_attn_fn=None):
     """One decoder layer on the model's own parameters (HF models/qwen3/modeling_qwen3.py:252-291, 81-83);
-    ``attn_fn(q, k, v, scaling)`` is the attention node."""
+    ``attn_fn(q, k, v, scaling)`` is the attention node, ``qk_attn_fn(q_raw, k_raw, v, wq, wk, scaling)`` the combined
+    q/k-norm + RoPE + attention node (used when given and the views allow it)."""
     at, mlp = layer.self_attn, layer.mlp
     h, residual = add_rmsnorm(x, residual, layer.input_layernorm.weight, eps)
     q, k, v = multi_linear(h, at.q_proj.weight, at.k_proj.weight, at.v_proj.weight)
     q, k, v = q.view(n, hq, d), k.view(n, hkv, d), v.view(n, hkv, d)
-    q, k = qknorm_rope(q, k, at.q_norm.weight, at.k_norm.weight, depth, table, eps)
-    a = attn_fn(q, k, v, at.scaling)
+    if qk_attn_fn is not None and _qk_fusable(q, k, v):
+        a = qk_attn_fn(q, k, v, at.q_norm.weight, at.k_norm.weight, at.scaling)
+    else:
+        q, k = qknorm_rope(q, k, at.q_norm.weight, at.k_norm.weight, depth, table, eps)
+        a = attn_fn(q, k, v, at.scaling)
     o = F.linear(a.view(n, hq * d), at.o_proj.weight)
     h, residual = add_rmsnorm(o, residual, layer.post_attention_layernorm.weight, eps)
     gate, up = multi_linear(h, mlp.gate_proj.weight, mlp.up_proj.weight)
@@ -261,8 +330,12 @@ class _RecomputedLayer(torch.autograd.Function):
         def attn_again(q, k, v, scaling):
             return TreeAttnFromSaved.apply(q, k, v, layout, scaling, out, lse)
 
+        def qk_attn_again(q, k, v, wq, wk, scaling):
+            return qknorm_rope_attention(q, k, v, wq, wk, depth, table, ctx.eps, layout, scaling, kept=(out, lse))
+
         with torch.enable_grad():
-            x_out, res_out = _layer_forward(ctx.layer, xd, rd, n, hq, hkv, d, depth, table, ctx.eps, attn_again)
+            x_out, res_out = _layer_forward(ctx.layer, xd, rd, n, hq, hkv, d, depth, table, ctx.eps, attn_again,
+                                            qk_attn_again)
         outs, grads = [], []
         for o, g in ((x_out, gx), (res_out, gres)):
             if g is not None:
@@ -286,10 +359,13 @@ def fused_trunk_forward(model, layout: TrieLayout, recompute: bool = False) -> t
     x = base.embed_tokens(layout.tok)                       # [N, hidden]
     residual = None
     attn = lambda q, k, v, scaling: tree_attention(q, k, v, layout, scaling)      # noqa: E731
+    qk_attn = None
+    if torch.is_grad_enabled():        # the combined node only changes the BACKWARD (fp32 dQ hand-over)
+        qk_attn = lambda q, k, v, wq, wk, scaling: qknorm_rope_attention(q, k, v, wq, wk, depth, table, eps, layout, scaling)   # noqa: E731
     for layer in base.layers:
         if recompute and torch.is_grad_enabled():
             x, residual = _RecomputedLayer.apply(x, residual, layer, layout, n, hq, hkv, d, depth, table, eps)
         else:
-            x, residual = _layer_forward(layer, x, residual, n, hq, hkv, d, depth, table, eps, attn)
+            x, residual = _layer_forward(layer, x, residual, n, hq, hkv, d, depth, table, eps, attn, qk_attn)
     h, _ = add_rmsnorm(x, residual, base.norm.weight, eps)
     return h

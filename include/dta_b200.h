@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTA_ABI_VERSION 6
+#define DTA_ABI_VERSION 7
 #define DTA_TILE 128 /* attention tile edge (queries and keys) */
 
 typedef struct CUstream_st* dta_stream_t;
@@ -154,6 +154,14 @@ int dta_tree_attn_bwd(const void* q, const void* k, const void* v, const void* o
                       const float* lse, void* dq, void* dk, void* dv, const dta_attn_meta_t* meta,
                       const dta_attn_shape_t* shape, void* workspace, dta_stream_t stream);
 
+/* Same backward with dQ left in fp32: dq_f32[n_pad, Hq, D] (16-byte aligned, contents need not be initialised) is used
+ * as the accumulator of the kernel's tensor reduce-adds and handed back as is — no bf16 dq tensor, no conversion pass.
+ * Consumer: dta_qknorm_rope_bwd_f32dq (the q/k-norm + RoPE backward sits right behind attention in the model,
+ * HF models/qwen3/modeling_qwen3.py:263-268). */
+int dta_tree_attn_bwd_f32dq(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                            const float* lse, float* dq_f32, void* dk, void* dv, const dta_attn_meta_t* meta,
+                            const dta_attn_shape_t* shape, void* workspace, dta_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Log-prob + entropy over a vocab shard — replaces _gather_logprobs[_entropy] and the
  * vocab-parallel autograd functions (reference vocab_parallel.py:13-27, 117-166, 249-321,
@@ -275,6 +283,15 @@ int dta_qknorm_rope_bwd(const void* dq_out, const void* dk_out, const void* q, i
                         int64_t n_rows, int n_q_heads, int n_kv_heads, int head_dim, void* dq, int64_t dq_row_stride,
                         int64_t dq_head_stride, void* dk, int64_t dk_row_stride, int64_t dk_head_stride, float* dwq,
                         float* dwk, dta_stream_t stream);
+
+/* dta_qknorm_rope_bwd with d q_out given in fp32, contiguous [n_rows, Hq, 128] (the accumulator dta_tree_attn_bwd_f32dq
+ * leaves behind); d k_out stays bf16.  Needs 16-byte aligned tensors and strides that are multiples of 8 elements. */
+int dta_qknorm_rope_bwd_f32dq(const float* dq_out_f32, const void* dk_out, const void* q, int64_t q_row_stride,
+                              int64_t q_head_stride, const void* k, int64_t k_row_stride, int64_t k_head_stride,
+                              const void* wq, const void* wk, const int32_t* depth, const float* cos_sin, const float* rstd,
+                              int64_t n_rows, int n_q_heads, int n_kv_heads, int head_dim, void* dq, int64_t dq_row_stride,
+                              int64_t dq_head_stride, void* dk, int64_t dk_row_stride, int64_t dk_head_stride, float* dwq,
+                              float* dwk, dta_stream_t stream);
 
 /* out = silu(gate) * up;  backward returns d gate and d up. */
 int dta_swiglu_fwd(const void* gate, const void* up, int64_t n_elems, void* out, dta_stream_t stream);

@@ -768,6 +768,48 @@ def test_qknorm_rope_fwd_bwd(hq, hkv, pad):
     assert _rel(got, bufr.grad) < 6e-3 and _rel(wq.grad, wqr.grad) < 6e-3 and _rel(wk.grad, wkr.grad) < 6e-3
 
 
+@pytest.mark.parametrize("name,hq,hkv", [("fan_small", 4, 2), ("tau2_mini", 16, 8), ("chain_129", 2, 1)])
+def test_qknorm_rope_attention_fused_backward(name, hq, hkv):
+    """The combined q/k-norm + RoPE + attention node (fp32 dQ accumulator handed straight to the q/k-norm backward:
+    dta_tree_attn_bwd_f32dq -> dta_qknorm_rope_bwd_f32dq) against the two separate nodes: identical forward, gradients
+    equal up to the one bf16 rounding of dq that the fused path skips; also with a kept (out, lse) pair, as a
+    recomputed layer calls it."""
+    from dynamictreeattn_b200.attention import tree_attention
+    from dynamictreeattn_b200.fused_layers import qknorm_rope, qknorm_rope_attention
+    trie, lay = _layout(name)
+    n, d = lay.n_nodes, 128
+    torch.manual_seed(0)
+    raw = torch.randn(n, (hq + 2 * hkv) * d, device="cuda").bfloat16()
+    wq0 = (1 + 0.1 * torch.randn(d, device="cuda")).bfloat16()
+    wk0 = (1 + 0.1 * torch.randn(d, device="cuda")).bfloat16()
+    depth = lay.depth[:n]
+    inv_freq = 1.0 / (1e6 ** (torch.arange(0, d, 2, device="cuda").float() / d))
+    fr = torch.arange(int(depth.max()) + 1, device="cuda").float()[:, None] * inv_freq[None]
+    table = torch.cat([fr.cos(), fr.sin()], 1).contiguous()
+    do = torch.randn(n, hq, d, device="cuda").bfloat16()
+    res = {}
+    for mode in ("separate", "fused", "fused_kept"):
+        x = raw.clone().requires_grad_(True)
+        wq, wk = wq0.clone().requires_grad_(True), wk0.clone().requires_grad_(True)
+        q = x[:, :hq * d].view(n, hq, d)
+        kk = x[:, hq * d:(hq + hkv) * d].view(n, hkv, d)
+        v = x[:, (hq + hkv) * d:].view(n, hkv, d)
+        if mode == "separate":
+            qr, kr = qknorm_rope(q, kk, wq, wk, depth, table, 1e-6)
+            out = tree_attention(qr, kr, v, lay, d ** -0.5)
+        elif mode == "fused":
+            out = qknorm_rope_attention(q, kk, v, wq, wk, depth, table, 1e-6, lay, d ** -0.5)
+        else:
+            out = qknorm_rope_attention(q, kk, v, wq, wk, depth, table, 1e-6, lay, d ** -0.5, kept=res["fused"][4])
+        lse = out.grad_fn.saved_tensors[-1] if mode == "fused" else None        # before backward frees the node
+        out.backward(do)
+        res[mode] = (out.detach(), x.grad, wq.grad, wk.grad, (out.detach(), lse))
+    assert torch.equal(res["separate"][0], res["fused"][0]) and torch.equal(res["fused"][0], res["fused_kept"][0])
+    for i in (1, 2, 3):
+        assert _rel(res["fused"][i], res["separate"][i]) < 6e-3, i
+        assert _rel(res["fused_kept"][i], res["fused"][i]) < 1e-3, i        # dQ is a sum of fp32 reduce-adds: order varies
+
+
 def test_multi_linear_matches_separate_linears():
     import torch.nn.functional as F
     from dynamictreeattn_b200.fused_layers import multi_linear
