@@ -94,6 +94,27 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.mm(a, b).float()
 
 
+_ADDMM_OUT_DTYPE = None
+
+
+def _addmm_f32_(acc: torch.Tensor, a: torch.Tensor, b: torch.Tensor) -> None:
+    """acc (fp32) += a @ b (bf16 operands) inside the GEMM's epilogue when the torch build can (``addmm`` with
+    ``out_dtype``): saves reading and writing the 0.6 GB fp32 dW accumulator once more per row chunk; otherwise an
+    fp32-output GEMM followed by an add."""
+    global _ADDMM_OUT_DTYPE
+    if _ADDMM_OUT_DTYPE is None:
+        try:
+            t = torch.zeros((1, 1), dtype=torch.float32, device=a.device)
+            torch.addmm(t, a[:1, :8], b[:8, :1], out_dtype=torch.float32, out=t)
+            _ADDMM_OUT_DTYPE = True
+        except (TypeError, RuntimeError):
+            _ADDMM_OUT_DTYPE = False
+    if _ADDMM_OUT_DTYPE:
+        torch.addmm(acc, a, b, out_dtype=torch.float32, out=acc)
+    else:
+        acc.add_(_mm_f32(a, b))
+
+
 class _EdgePlan:
     """Edges (parent row -> child node) grouped by parent row, so a chunk of logits rows
     maps to one contiguous run of labels."""
@@ -188,7 +209,7 @@ class _TreeHeadLoss(torch.autograd.Function):
                 if need_h:
                     torch.mm(logits, W, out=dh[a:b])
                 if need_w:
-                    dW32.add_(_mm_f32(logits.t(), h[a:b]))
+                    _addmm_f32_(dW32, logits.t(), h[a:b])
                 del logits
         ctx.dh = dh
         ctx.dW = dW32.to(W.dtype) if need_w else None
