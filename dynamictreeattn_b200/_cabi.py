@@ -18,7 +18,7 @@ import torch
 _LIB_PATH = Path(os.environ.get("DTA_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libdta_b200.so")
 _lib = None
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 TILE = 128
 
 
@@ -57,6 +57,7 @@ SIGNATURES = {
     "dta_tile_meta": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dta_trie_build_workspace_bytes": (_Z, [_I]),
     "dta_trie_build": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "dta_host_subtrie_stats": (_I, [_P, _P, _I, _I, _L, _P]),
     "dta_tree_attn_fwd": (_I, [_P, _P, _P, _P, _P, C.POINTER(AttnMeta), C.POINTER(AttnShape), _P]),
     "dta_profile_next_attn": (_I, [_P, _P]),
     "dta_tree_attn_bwd_workspace_bytes": (_Z, [C.POINTER(AttnShape)]),

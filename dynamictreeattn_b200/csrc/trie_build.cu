@@ -337,3 +337,155 @@ int dta_trie_build(const int64_t* tokens, const int64_t* offsets, int n_seq, int
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// HOST-side planning helper for the partitioner (no device work).  LB_by_DFS_and_TM (reference data_parallel.py:58-107)
+// probes a few hundred contiguous leaf ranges per call; every probe builds the range's compressed trie, orders its
+// leaves (trie.py:190-202, 225-233) and evaluates _get_stats (trie.py:7-56).  In Python that is ~100 us per probe and the
+// whole partition 20-40 ms of a ~800 ms step at 8 GPUs; here it is the same algorithm, verbatim, in C++ (a few us).
+// Results are integers and must equal the Python code's bit for bit (tests/test_host_golden.py).
+// ------------------------------------------------------------------------------------
+#include <vector>
+
+namespace dta {
+namespace host_plan {
+
+struct Trie {
+  std::vector<int> depth, seq_id, head, tail_child, next, tail;
+  int add(int d, int s) {
+    depth.push_back(d); seq_id.push_back(s); head.push_back(-1); tail_child.push_back(-1); next.push_back(-1); tail.push_back(0);
+    return static_cast<int>(depth.size()) - 1;
+  }
+  void append(int v, int c) {
+    next[c] = -1;
+    if (tail_child[v] < 0) head[v] = c; else next[tail_child[v]] = c;
+    tail_child[v] = c;
+  }
+  long long key(int c, bool backward) const {
+    const long long fork = (backward && head[c] >= 0) ? 1 : 0;
+    return (fork << 32) | static_cast<unsigned>(tail[c]);
+  }
+};
+
+static void build(Trie& t, const int32_t* lens, const int32_t* lcps, int n_leaf) {
+  t.add(0, -1);
+  std::vector<int> spine{0};
+  for (int i = 0; i < n_leaf; ++i) {
+    const int f = i > 0 ? lcps[i - 1] : 0;
+    int closed = -1;
+    while (spine.size() > 1 && (t.depth[spine.back()] > f || t.seq_id[spine.back()] != -1)) {
+      const int v = spine.back();
+      spine.pop_back();
+      if (closed >= 0) t.append(v, closed);
+      closed = v;
+    }
+    if (t.depth[spine.back()] < f) spine.push_back(t.add(f, -1));
+    if (closed >= 0) t.append(spine.back(), closed);
+    spine.push_back(t.add(lens[i], i));
+  }
+  while (spine.size() > 1) {
+    const int v = spine.back();
+    spine.pop_back();
+    t.append(spine.back(), v);
+  }
+}
+
+// leaves in DFS order with children sorted stably by key; lens / lcps as trie.py's _walk emits them (lcp = shallowest node
+// depth crossed since the previous leaf)
+static void order(Trie& t, bool backward, std::vector<int>& lens, std::vector<int>& lcps) {
+  std::vector<std::pair<int, int>> st{{0, t.head[0]}};
+  while (!st.empty()) {                      // tails, post-order (trie.py:135-148)
+    const int v = st.back().first;
+    if (t.seq_id[v] != -1) { t.tail[v] = t.depth[v]; st.pop_back(); continue; }
+    const int c = st.back().second;
+    if (c != -1) {
+      st.back().second = t.next[c];
+      st.push_back({c, t.head[c]});
+    } else {
+      int best = t.head[v];
+      for (int k = t.next[best]; k != -1; k = t.next[k])
+        if (t.key(k, backward) < t.key(best, backward)) best = k;
+      t.tail[v] = t.tail[best];
+      st.pop_back();
+    }
+  }
+  int lca = 0;
+  std::vector<std::pair<int, int>> todo{{0, -1}};   // (node, parent depth)
+  std::vector<int> kids;
+  while (!todo.empty()) {
+    const int v = todo.back().first, pd = todo.back().second;
+    todo.pop_back();
+    if (pd >= 0 && pd < lca) lca = pd;
+    if (t.seq_id[v] != -1) {
+      lens.push_back(t.depth[v]);
+      lcps.push_back(lca);
+      lca = t.depth[v];
+      continue;
+    }
+    kids.clear();
+    for (int k = t.head[v]; k != -1; k = t.next[k]) {   // stable insertion sort by key
+      kids.push_back(k);
+      size_t p = kids.size() - 1;
+      while (p > 0 && t.key(kids[p - 1], backward) > t.key(k, backward)) { kids[p] = kids[p - 1]; --p; }
+      kids[p] = k;
+    }
+    for (size_t p = kids.size(); p-- > 0;) todo.push_back({kids[p], t.depth[v]});
+  }
+}
+
+}  // namespace host_plan
+}  // namespace dta
+
+extern "C" int dta_host_subtrie_stats(const int32_t* lens, const int32_t* lcps, int n_leaf, int backward, int64_t block_size,
+                                      int64_t* out5) {
+  using namespace dta::host_plan;
+  if (!lens || !out5 || n_leaf < 1 || (n_leaf > 1 && !lcps)) return 1;
+  Trie t;
+  build(t, lens, lcps, n_leaf);
+  std::vector<int> L, C;
+  order(t, backward != 0, L, C);
+  // get_order_forward: (lens, lcp[1:]); get_order_backward: (lens[::-1], lcp[1:][::-1])   (trie.py:225-233)
+  std::vector<int> lcp(C.begin() + 1, C.end());
+  if (backward) {
+    std::vector<int> Lr(L.rbegin(), L.rend()), Cr(lcp.rbegin(), lcp.rend());
+    L.swap(Lr);
+    lcp.swap(Cr);
+  }
+  // _get_stats (trie.py:7-56), with the last-leaf lcp read as 0 where the reference raises IndexError
+  long long n_tree = 0, sum_depth = 0, sum_prefix = 0, n_f1 = 0;
+  for (int i = 0; i < n_leaf; ++i) n_tree += L[i];
+  for (size_t i = 0; i < lcp.size(); ++i) n_tree -= lcp[i];
+  for (int i = 0; i < n_leaf; ++i) {
+    const long long lo = i > 0 ? lcp[i - 1] : 0, hi = L[i];
+    sum_depth += (lo + hi - 1) * (hi - lo) / 2;
+  }
+  if (!backward) {
+    for (size_t i = 0; i < lcp.size(); ++i) sum_prefix += lcp[i];
+  } else {
+    for (int i = 0; i < n_leaf; ++i) {
+      const long long keep = i < static_cast<int>(lcp.size()) ? lcp[i] : 0, hi = L[i];
+      const long long popped = hi - keep, pushed_from = i > 0 ? lcp[i - 1] : 0;
+      long long f1_end;
+      if (block_size <= 0 || popped <= block_size) {
+        f1_end = keep;
+        sum_prefix += keep;
+      } else {
+        const long long n_blocks = (popped + block_size - 1) / block_size;
+        const long long blk = (popped + n_blocks - 1) / n_blocks;
+        f1_end = hi - blk;
+        for (long long b = 0; b < n_blocks; ++b) {
+          const long long x = hi - (b + 1) * blk;
+          sum_prefix += x > keep ? x : keep;
+        }
+      }
+      const long long d = f1_end - pushed_from;
+      n_f1 += d > 0 ? d : 0;
+    }
+  }
+  out5[0] = n_leaf;
+  out5[1] = n_tree;
+  out5[2] = sum_prefix;
+  out5[3] = sum_depth;
+  out5[4] = n_f1;
+  return 0;
+}

@@ -63,6 +63,49 @@ def pred_time(compressed_trie: CompressedTrie, time_model, mode: str,
     return time_model.pred(_get_stats(lens, lcp_lens, mode, block_size))
 
 
+def _native_range_stats(compressed_trie: CompressedTrie, start: int, end: int, mode: str,
+                        block_size: Optional[int]) -> Optional[dict]:
+    """``_get_stats`` of the sub-trie of leaves [start, end) in its planned order, from the C++ host helper of the
+    kernel library (``dta_host_subtrie_stats``: the same integer algorithm as trie.py, ~100x faster); None when the
+    library is not built (the Python path then does the work)."""
+    import ctypes as C
+    try:
+        import numpy as np
+        from . import _cabi
+        lib = _cabi.load(build_if_missing=False)
+    except Exception:  # noqa: BLE001  (no library: pure-Python planning still works)
+        return None
+    cache = getattr(compressed_trie, "_np_leaves", None)
+    if cache is None:
+        cache = (np.asarray(compressed_trie.leaf_lens, dtype=np.int32), np.asarray(compressed_trie.leaf_lcps, dtype=np.int32))
+        compressed_trie._np_leaves = cache
+    lens, lcps = cache
+    n = end - start
+    out = np.empty(5, dtype=np.int64)
+    lens_p = lens[start:end].ctypes.data_as(C.c_void_p)
+    lcps_p = lcps[start:end - 1].ctypes.data_as(C.c_void_p) if n > 1 else None
+    rc = lib.dta_host_subtrie_stats(lens_p, lcps_p, n, 1 if mode == "backward" else 0,
+                                    int(block_size) if block_size else 0, out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        return None
+    stats = {"n_leaf_sequences": int(out[0]), "n_tree_tokens": int(out[1]), "sum_prefix_len": int(out[2]),
+             "sum_depth": int(out[3])}
+    if mode == "backward":
+        stats["n_f1_tokens"] = int(out[4])
+    return stats
+
+
+def pred_time_range(compressed_trie: CompressedTrie, start: int, end: int, time_model, mode: str,
+                    block_size: Optional[int] = None) -> float:
+    """``pred_time(_get_subtrie(trie, set(range(start, end))), ...)`` for a contiguous range of the trie's leaves."""
+    if mode not in ("forward", "backward"):
+        raise ValueError(f"Unsupported mode: {mode}")
+    stats = _native_range_stats(compressed_trie, start, end, mode, block_size)
+    if stats is None:
+        return pred_time(_get_range_subtrie(compressed_trie, start, end), time_model, mode, block_size)
+    return time_model.pred(stats)
+
+
 def get_original_bins(token_trie: TokenTrie, leaf_bins: List[List[int]]) -> List[List[int]]:
     """Leaf indices -> original sequence indices via the attach lists (data_parallel.py:29-37)."""
     return [
@@ -107,8 +150,8 @@ def try_devide(compressed_trie, n_seqs, args, divL, divR, time_model, cost_limit
             mid = (lo + hi + 1) // 2
             cost = _cost_cache.get((start, mid)) if _cost_cache is not None else None
             if cost is None:
-                sub = _get_range_subtrie(compressed_trie, start, mid + 1)      # == _get_subtrie(trie, set(range(start, mid + 1)))
-                cost = pred_time(sub, time_model, args.mode, args.block_size)
+                # == pred_time(_get_subtrie(trie, set(range(start, mid + 1))), ...)
+                cost = pred_time_range(compressed_trie, start, mid + 1, time_model, args.mode, args.block_size)
                 if _cost_cache is not None:
                     _cost_cache[(start, mid)] = cost
             if cost <= cost_limit:

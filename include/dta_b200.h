@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DTA_ABI_VERSION 7
+#define DTA_ABI_VERSION 8
 #define DTA_TILE 128 /* attention tile edge (queries and keys) */
 
 typedef struct CUstream_st* dta_stream_t;
@@ -86,6 +86,15 @@ int dta_trie_paths(const int32_t* lens, const int32_t* lcp, const int32_t* leaf_
 size_t dta_trie_build_workspace_bytes(int n_seq);
 int dta_trie_build(const int64_t* tokens, const int64_t* offsets, int n_seq, int presorted, void* workspace,
                    int32_t* out, dta_stream_t stream);
+
+/* HOST function (no device work; every pointer is a HOST pointer): cost-model features of the sub-trie spanned by the
+ * DFS-ordered leaves (lens[n_leaf], lcps[n_leaf - 1]) in the order get_order_forward (backward = 0) or
+ * get_order_backward (backward != 0) visits them — reference trie.py:190-202, 225-233 followed by _get_stats
+ * (trie.py:7-56; block_size <= 0 means None).  out5 = {n_leaf_sequences, n_tree_tokens, sum_prefix_len, sum_depth,
+ * n_f1_tokens (0 in forward mode)}.  Used by the partitioner's probes (LB_by_DFS_and_TM, data_parallel.py:58-79):
+ * the same integers as the Python code, ~100x faster. */
+int dta_host_subtrie_stats(const int32_t* lens, const int32_t* lcps, int n_leaf, int backward, int64_t block_size,
+                           int64_t* out5);
 
 /* Per-tile mask summaries and work orders for the attention kernels (n_tiles = n_pad/DTA_TILE):
  *   kmax_end[t], kmin_end[t] : max / min of subtree_end over the VALID keys of tile t

@@ -117,6 +117,25 @@ def test_range_subtrie_equals_subset_subtrie(idx):
             assert x.get_order_backward() == y.get_order_backward()
 
 
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_native_range_stats_equal_python(idx):
+    """dta_host_subtrie_stats (C++ host helper of the partitioner's probes) returns the integers of the Python code —
+    sub-trie -> get_order_forward / get_order_backward -> _get_stats — for every contiguous leaf range, every mode and
+    block size (incl. the cases where the reference raises IndexError, where both use the intended value 0)."""
+    c = CASES[idx]
+    t = TokenTrie(_seqs(c))
+    full = CompressedTrie(t.lens, t.lcp_lens)
+    n = len(t.lens)
+    for a in range(n):
+        for b in range(a + 1, n + 1):
+            sub = _get_subtrie(full, set(range(a, b)))
+            for mode, bs in (("forward", None), ("backward", None), ("backward", 3), ("backward", 2048)):
+                _, lens, lcps = sub.get_order_forward() if mode == "forward" else sub.get_order_backward()
+                want = _get_stats(lens, lcps, mode, bs)
+                got = dp._native_range_stats(full, a, b, mode, bs)
+                assert got is not None and got == want, (a, b, mode, bs)
+
+
 def test_time_model_matches_reference():
     g = json.loads((GOLDEN / "time_model.json").read_text())
     tm = TreeTimeModel()
