@@ -27,6 +27,7 @@ SOURCES = [
     "logprob_kernels.cu",
     "head_fwd.cu",
     "attn_fwd.cu",
+    "attn_fwd_persist.cu",
     "attn_bwd.cu",
     "attn_bwd_pair.cu",
     "layer_kernels.cu",

@@ -21,51 +21,11 @@
 //                  softmax of one tile overlaps the tensor work of the other.
 //   softmax      = online, base-2, lazy rescale (O is rescaled only when the row max grows
 //                  by more than 2^8), one thread per query row -> no shuffles.
-#include "dta_common.cuh"
-#include "dta_ptx.cuh"
-#include "../../include/dta_b200.h"
+#include "attn_fwd.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace dta {
-
-static constexpr int kBM = 128;       // queries per tile
-static constexpr int kBN = 128;       // keys per tile
-static constexpr int kD = 128;        // head dim
-static constexpr int kHalfBytes = kBM * 128;          // one [128 rows][64 bf16] swizzled half-tile
-static constexpr int kTileBytes = 2 * kHalfBytes;     // 32 KB
-static constexpr int kStages = 2;
-static constexpr int kFwdThreads = 384;
-static constexpr int kProducerWarp = 10, kMmaWarp = 11;
-static constexpr int kMaxLive = 4096;
-static constexpr float kLog2e = 1.4426950408889634f;
-static constexpr float kLn2 = 0.6931471805599453f;
-static constexpr float kRescaleThreshold = 8.0f;      // log2 units
-static constexpr int kDefaultFwdPoly = 2;             // of every 8 exponentials, on the FMA pipes
-
-struct FwdSmem {
-  // offsets inside the 1024-aligned dynamic shared buffer
-  static constexpr int q = 0;                                  // 2 tiles
-  static constexpr int k = q + 2 * kTileBytes;                 // kStages tiles
-  static constexpr int v = k + kStages * kTileBytes;           // kStages tiles
-  static constexpr int live = v + kStages * kTileBytes;        // int32[kMaxLive]
-  static constexpr int bars = live + kMaxLive * 4;             // mbarriers
-  static constexpr int n_bars = 1 + 4 * kStages + 6;
-  static constexpr int misc = bars + n_bars * 8;               // tmem addr, n_live
-  static constexpr int total = misc + 16;
-};
-
-struct FwdParams {
-  __nv_bfloat16* out;
-  float* lse;
-  const int32_t* subtree_end;
-  const int32_t* kmax_end;
-  const int32_t* kmin_end;
-  const int32_t* q_order;
-  int n_nodes, n_pad, n_tiles;
-  int n_q_heads, n_kv_heads, group, pairs_per_kv;
-  int64_t o_row_stride, o_head_stride;
-  float scale_log2;
-};
 
 // kPolyOf8: how many of every 8 exponentials run on the FMA pipes (poly_exp2) instead of MUFU
 // kHeadMajor: launch order.  false: the head pairs of a query tile side by side (all KV heads resident at once);
@@ -419,6 +379,16 @@ extern "C" int dta_tree_attn_fwd(const void* q, const void* k, const void* v, vo
   p.o_row_stride = sh->o_row_stride;
   p.o_head_stride = sh->o_head_stride;
   p.scale_log2 = sh->scale * kLog2e;
+
+  // Default: the persistent kernel (attn_fwd_persist.cu) -- faster on every shape of the config-5 sweep and on the tau2
+  // trie, 1.3-1.8x on bushy tries (profiles/r02/attn_sweep_persist.jsonl).  The one-item-per-CTA kernel below serves
+  // tries of more than kPersistMaxTiles tiles (262,144 tokens) and DTA_FWD_PERSIST=0 (A/B runs, the bit-equality test).
+  const char* pe = getenv("DTA_FWD_PERSIST");               // read per call: tests and A/B runs switch it in-process
+  const bool persist = !(pe && *pe && strcmp(pe, "auto") != 0 && atoi(pe) == 0);
+  if (persist && p.n_tiles <= kPersistMaxTiles) {
+    const char* e = getenv("DTA_FWD_POLY");
+    return launch_tree_attn_fwd_persist(tq, tk, tv, p, e ? atoi(e) : kDefaultFwdPoly, stream, take_profile_hook());
+  }
 
   const int smem_bytes = FwdSmem::total + 1024;
   using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);

@@ -68,6 +68,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait bounded by TIME (~2 s of SM clock) instead of a try count: with the 10 ms suspend hint above a try count bounds
+// nothing a test run would wait for.  For kernels whose barrier protocol is new: a protocol bug traps within seconds.
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity) {
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > (1ll << 32)) {
+      printf("dta: mbarrier timeout block=%d thread=%d bar=%u parity=%u\n", blockIdx.x, threadIdx.x, smem_u32(bar) & 1023u,
+             parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------
 // proxies / fences
 // ----------------------------------------------------------------------------

@@ -458,6 +458,39 @@ def test_attention_parity_at_benchmarked_shapes(name, pair, monkeypatch):
     assert errs["out"] < 5e-3 and errs["dq"] < 1e-2 and errs["dk"] < 1e-2 and errs["dv"] < 1e-2, errs
 
 
+@pytest.mark.parametrize("name,heads", [("single_token", (2, 1)), ("chain_129", (2, 1)), ("chain_300", (4, 2)),
+                                        ("fan_small", (4, 2)), ("deep_forks", (3, 1)), ("forest", (3, 3)),
+                                        ("adversarial", (4, 2)), ("many_leaves", (6, 2)), ("tau2_mini", (16, 8)),
+                                        ("bench:fan_p0_b64", (16, 8)), ("bench:bary_b64", (16, 8)),
+                                        ("bench:fan_p4096_b16", (4, 2))])
+def test_persistent_forward_equals_one_item_per_cta_kernel(name, heads, monkeypatch):
+    """The persistent forward (csrc/attn_fwd_persist.cu: one CTA per SM drawing items from a counter, the default for
+    bushy tries) runs the same per-item arithmetic in the same key-tile order as the one-item-per-CTA kernel, so out
+    and lse are BIT-equal -- on odd GQA groups (the last pair of a KV head has one query head), MHA, and over
+    repeated launches (the work counters re-arm themselves)."""
+    from dynamictreeattn_b200.attention import tree_attention_forward
+    from dynamictreeattn_b200.linearize import linearize_trie
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    if name.startswith("bench:"):
+        trie = TokenTrie(_bench_shape(name[6:]))
+        trie.backward_permute()
+        lay = linearize_trie(trie, "cuda")
+    else:
+        trie, lay = _layout(name)
+    Hq, Hkv = heads
+    q, k, v, _ = _qkv(lay.n_nodes, Hq, Hkv)
+    monkeypatch.setenv("DTA_FWD_PERSIST", "0")
+    _, _, _, out0, lse0 = tree_attention_forward(q, k, v, lay, 128 ** -0.5)
+    monkeypatch.setenv("DTA_FWD_PERSIST", "1")
+    for _ in range(3):
+        _, _, _, out1, lse1 = tree_attention_forward(q, k, v, lay, 128 ** -0.5)
+        assert torch.equal(out0, out1)
+        assert torch.equal(lse0[:, :lay.n_nodes], lse1[:, :lay.n_nodes])
+    monkeypatch.delenv("DTA_FWD_PERSIST")
+    _, _, _, out2, lse2 = tree_attention_forward(q, k, v, lay, 128 ** -0.5)     # the automatic choice
+    assert torch.equal(out0, out2) and torch.equal(lse0[:, :lay.n_nodes], lse2[:, :lay.n_nodes])
+
+
 def test_tree_attention_strided_views_and_lse():
     """q/k/v as HF hands them over: transposed views of one fused projection buffer."""
     from dynamictreeattn_b200.attention import TreeAttnFunction

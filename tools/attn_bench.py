@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import os
 import statistics
 import sys
 from pathlib import Path
@@ -51,6 +52,19 @@ def run_case(name, seqs, iters, Hq=16, Hkv=8, permute="backward"):
     torch.cuda.synchronize()
     fwd = [a.elapsed_time(b) for kind, a, b in attention.PROFILE if kind == "fwd"]
     bwd = [a.elapsed_time(b) for kind, a, b in attention.PROFILE if kind == "bwd"]
+    # the two forward kernels side by side (the call above takes the default: persistent up to 2048 tiles)
+    fwd_ab = {}
+    for mode in ("0", "1"):
+        os.environ["DTA_FWD_PERSIST"] = mode
+        with torch.no_grad():
+            for _ in range(2):
+                attention.tree_attention_forward(q, k, v, lay, 128 ** -0.5)
+            attention.PROFILE = []
+            for _ in range(max(iters, 5)):
+                attention.tree_attention_forward(q, k, v, lay, 128 ** -0.5)
+        torch.cuda.synchronize()
+        fwd_ab[mode] = statistics.median(a.elapsed_time(b) for _, a, b in attention.PROFILE)
+    os.environ.pop("DTA_FWD_PERSIST")
     attention.PROFILE = None
     f, b = statistics.median(fwd), statistics.median(bwd)
     # tile density: visible pairs / (live 128 x 128 tile pairs x 128^2) -- how much of the tensor work the kernels issue
@@ -68,7 +82,9 @@ def run_case(name, seqs, iters, Hq=16, Hkv=8, permute="backward"):
            "fwd_ms": round(f, 3), "bwd_ms": round(b, 3),
            "fwd_min_ms": round(min(fwd), 3), "bwd_min_ms": round(min(bwd), 3),
            "fwd_tflops": round(4 * P * Hq * 128 / f / 1e9, 1), "bwd_tflops": round(10 * P * Hq * 128 / b / 1e9, 1),
-           "fwd_bwd_tflops": round(14 * P * Hq * 128 / (f + b) / 1e9, 1)}
+           "fwd_bwd_tflops": round(14 * P * Hq * 128 / (f + b) / 1e9, 1),
+           "fwd_one_item_per_cta_tflops": round(4 * P * Hq * 128 / fwd_ab["0"] / 1e9, 1),
+           "fwd_persistent_tflops": round(4 * P * Hq * 128 / fwd_ab["1"] / 1e9, 1)}
     print(json.dumps(res), flush=True)
     return res
 
@@ -90,15 +106,21 @@ def main():
     elif args.case == "bary":
         import math
         run_case(f"bary_b{args.b}", bary(args.n, args.b, max(1, math.ceil(math.log(64, args.b)))), args.iters)
+    elif args.case == "bushy":           # the short-item end of the sweep plus the two dense anchors
+        import math
+        for p, b in ((0, 1), (0, 8), (0, 16), (0, 32), (0, 64), (1024, 16), (1024, 64), (4096, 64)):
+            run_case(f"fan_p{p}_b{b}", trunk_fan(args.n, p, b), args.iters)
+        for b in (2, 8, 64):
+            run_case(f"bary_b{b}", bary(args.n, b, max(1, math.ceil(math.log(64, b)))), args.iters)
+        run_case("tau2", synth_trie(0, 6144, (4, 2, 2), (1024, 3072), vocab=151936, max_depth=16384), args.iters)
     elif args.case == "sweep":
         import math
         for p in (0, 1024, 4096, 8192, 12288):
             for b in (1, 2, 4, 8, 16, 32, 64):
-                if p == 0 and b > 1:
-                    pass
                 run_case(f"fan_p{p}_b{b}", trunk_fan(args.n, p, b), args.iters)
         for b in (2, 4, 8, 64):
             run_case(f"bary_b{b}", bary(args.n, b, max(1, math.ceil(math.log(64, b)))), args.iters)
+        run_case("tau2", synth_trie(0, 6144, (4, 2, 2), (1024, 3072), vocab=151936, max_depth=16384), args.iters)
 
 
 if __name__ == "__main__":
