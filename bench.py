@@ -798,6 +798,9 @@ def run_ours(args):
             "peak_source": peaks["source"],
             "flops_per_launch": bwd_flops, "ms_per_launch": bwd_mean,
             "attn_fwd_tflops": attn_fwd_tflops, "attn_fwd_ms_per_launch": fwd_mean,
+            "attn_fwd_kernel": ("tree_attn_fwd_kernel" if os.environ.get("DTA_FWD_PERSIST", "auto") in ("0",)
+                                or layout.n_pad // 128 > 2048 else "tree_attn_fwd_persist_kernel"),
+            "attn_fwd_frac_sustained": attn_fwd_tflops / peaks["sustained"],
             "attn_fwd_frac_burst": attn_fwd_tflops / peaks["burst"],
             "attn_fwd_bwd_tflops": (bwd_flops + fwd_flops) / ((bwd_mean + fwd_mean) / 1e3) / 1e12,
             "attn_share_of_step": attn_share,

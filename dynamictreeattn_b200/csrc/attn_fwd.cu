@@ -381,7 +381,7 @@ extern "C" int dta_tree_attn_fwd(const void* q, const void* k, const void* v, vo
   p.scale_log2 = sh->scale * kLog2e;
 
   // Default: the persistent kernel (attn_fwd_persist.cu) -- faster on every shape of the config-5 sweep and on the tau2
-  // trie, 1.3-1.8x on bushy tries (profiles/r02/attn_sweep_persist.jsonl).  The one-item-per-CTA kernel below serves
+  // trie, 1.3-1.8x on bushy tries (profiles/r02/attn_sweep_config5_persist.jsonl).  The one-item-per-CTA kernel below serves
   // tries of more than kPersistMaxTiles tiles (262,144 tokens) and DTA_FWD_PERSIST=0 (A/B runs, the bit-equality test).
   const char* pe = getenv("DTA_FWD_PERSIST");               // read per call: tests and A/B runs switch it in-process
   const bool persist = !(pe && *pe && strcmp(pe, "auto") != 0 && atoi(pe) == 0);

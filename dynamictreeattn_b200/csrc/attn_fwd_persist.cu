@@ -4,7 +4,7 @@
 // file's header first.  Why: a (query tile, head pair) item of a bushy trie sees one to ten key tiles, and the other
 // kernel then spends most of its time in CTA prologue and epilogue (fan(0, 64): 1.5 key tiles per item, 177 TFLOP/s;
 // 318 here); on the 67k-token tau2 trie the hidden prologue / epilogue and the shared-memory epilogue are worth 13 %
-// alone and 6 % inside the step (profiles/r02/attn_sweep_persist.jsonl, bench_ab9_*.json).  What changes:
+// alone and 6 % inside the step (profiles/r02/attn_sweep_config5_persist.jsonl, bench_ab9_*.json).  What changes:
 //
 //   grid         = one CTA per SM; the producer warp draws items from a global counter (atomicAdd), in the same
 //                  heaviest-first, head-major order the other kernel is launched in.  An item is claimed when the
