@@ -1,10 +1,11 @@
 // attn_bwd_pair.cu — CTA-PAIR variant of the tree attention backward main kernel (tcgen05 cta_group::2).
 //
-// EXPERIMENTAL: reached only when the environment holds DTA_BWD_PAIR=1 (dta_tree_attn_bwd, attn_bwd.cu); the
-// single-CTA kernel stays the default until this one is parity-green and faster on the B200.  Same mathematics,
-// same pre-pass (attn_delta_kernel) and epilogue (attn_dq_convert_kernel), same TMEM plan and warp roles as
-// attn_bwd.cu -- read that file's header first.  What changes (docs/next_kernels.md section 1; building blocks
-// verified by tools/umma_2cta.cu and tools/umma_2cta_probe2.cu):
+// The DEFAULT backward for launches the caller marks balanced (dta_attn_shape_t::bwd_whole_tiles: tau2, chains, deep
+// fans); the single-CTA work-list kernel (attn_bwd.cu) serves bushy tries, whose long-pole key tiles it splits, and
+// DTA_BWD_PAIR=0|1 forces either.  Measured in the power-capped step on one box: 921-941 TFLOP/s against 891-905 for
+// the single-CTA kernel.  Same mathematics, same pre-pass (attn_delta_kernel) and epilogue
+// (attn_dq_convert_kernel), same TMEM plan and warp roles as attn_bwd.cu -- read that file's header first.  What
+// changes (docs/next_kernels.md section 1; building blocks verified by tools/umma_2cta.cu and tools/umma_2cta_probe2.cu):
 //
 //   cluster (2,1,1) = key tiles (2j, 2j+1) x one KV head.  Both CTAs walk the UNION of the two tiles' live query
 //   ranges in lock-step (a step that one of the tiles cannot see is fully masked for that CTA: P^T = 0).
