@@ -491,6 +491,31 @@ def test_persistent_forward_equals_one_item_per_cta_kernel(name, heads, monkeypa
     assert torch.equal(out0, out2) and torch.equal(lse0[:, :lay.n_nodes], lse2[:, :lay.n_nodes])
 
 
+def test_persistent_forward_at_its_tile_limit(monkeypatch):
+    """2048 query tiles (a 262,144-token chain, every key tile live): the largest trie the persistent forward takes --
+    an item's live-tile list fills its slot and the 16-bit entries reach their top value.  Bit-equal to the
+    one-item-per-CTA kernel, which also serves the next size up (2049 tiles) on its own."""
+    from dynamictreeattn_b200.attention import tree_attention_forward
+    from dynamictreeattn_b200.linearize import linearize_trie
+    from dynamictreeattn_b200.token_trie import TokenTrie
+    g = torch.Generator().manual_seed(3)
+    for n_tok in (2048 * 128, 2048 * 128 + 5):
+        trie = TokenTrie([torch.randint(0, 50000, (n_tok,), generator=g)])
+        lay = linearize_trie(trie, "cuda")
+        q, k, v, _ = _qkv(lay.n_nodes, 2, 1)
+        monkeypatch.setenv("DTA_FWD_PERSIST", "0")
+        _, _, _, out0, lse0 = tree_attention_forward(q, k, v, lay, 128 ** -0.5)
+        monkeypatch.delenv("DTA_FWD_PERSIST")
+        _, _, _, out1, lse1 = tree_attention_forward(q, k, v, lay, 128 ** -0.5)
+        assert torch.equal(out0, out1) and torch.equal(lse0[:, :lay.n_nodes], lse1[:, :lay.n_nodes])
+        assert torch.isfinite(out1.float()).all()
+        # last row attends to everything before it: against fp32 on that one row
+        qf, kf, vf = q[-1, 0].float(), k[:, 0].float(), v[:, 0].float()
+        ref = torch.softmax((kf @ qf) * 128 ** -0.5, 0) @ vf
+        assert _rel(out1[-1, 0], ref) < 5e-3
+        del q, k, v, out0, out1
+
+
 def test_tree_attention_strided_views_and_lse():
     """q/k/v as HF hands them over: transposed views of one fused projection buffer."""
     from dynamictreeattn_b200.attention import TreeAttnFunction
