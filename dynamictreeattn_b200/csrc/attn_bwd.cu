@@ -116,7 +116,8 @@ template <int kPolyOf8, bool kDqTma, bool kWorkList>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                     const __grid_constant__ CUtensorMap tmap_dq, const BwdParams p) {
+                     const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_dk,
+                     const __grid_constant__ CUtensorMap tmap_dv, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem + BwdSmem::k;
   uint8_t* sV = smem + BwdSmem::v;
@@ -506,31 +507,49 @@ tree_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
       }
     } else {
-      __nv_bfloat16* dv_row = p.dv + static_cast<int64_t>(k_idx) * p.v_row_stride + static_cast<int64_t>(kvh) * p.v_head_stride + ch * 64;
-      __nv_bfloat16* dk_row = p.dk + static_cast<int64_t>(k_idx) * p.k_row_stride + static_cast<int64_t>(kvh) * p.k_head_stride + ch * 64;
+      // dV and dK leave through shared memory and a TMA store each: a thread owns one key row, so storing its 128
+      // bytes straight to global memory makes every store instruction touch 32 rows (measured on the forward:
+      // 7,100 cycles of LSU time per tile pair, csrc/attn_fwd_persist.cu).  Staging = the two Q stages, dead now that
+      // every MMA has retired: [128 keys][64 d] halves with the 128-byte swizzle the tensor map expects; rows past
+      // n_nodes are clipped by the store.
+      const uint32_t st_v = smem_u32(sQ) + ch * kHalf, st_k = smem_u32(sQ) + kTile + ch * kHalf;
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
         uint32_t a[32], b[32];
         tmem_ld_x32(RdV + lane_addr + ch * 64 + part * 32, a);
         tmem_ld_x32(RdK + lane_addr + ch * 64 + part * 32, b);
         tmem_ld_wait();
-        if (k_idx < p.n_nodes) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 w;
-            const float is = p.inv_scale;      // P^T was carried pre-multiplied by scale
-            w.x = pack_bf16x2(__uint_as_float(a[i + 0]) * is, __uint_as_float(a[i + 1]) * is);
-            w.y = pack_bf16x2(__uint_as_float(a[i + 2]) * is, __uint_as_float(a[i + 3]) * is);
-            w.z = pack_bf16x2(__uint_as_float(a[i + 4]) * is, __uint_as_float(a[i + 5]) * is);
-            w.w = pack_bf16x2(__uint_as_float(a[i + 6]) * is, __uint_as_float(a[i + 7]) * is);
-            *reinterpret_cast<uint4*>(dv_row + part * 32 + i) = w;
-            w.x = pack_bf16x2(__uint_as_float(b[i + 0]), __uint_as_float(b[i + 1]));
-            w.y = pack_bf16x2(__uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
-            w.z = pack_bf16x2(__uint_as_float(b[i + 4]), __uint_as_float(b[i + 5]));
-            w.w = pack_bf16x2(__uint_as_float(b[i + 6]), __uint_as_float(b[i + 7]));
-            *reinterpret_cast<uint4*>(dk_row + part * 32 + i) = w;
-          }
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          const float is = p.inv_scale;      // P^T was carried pre-multiplied by scale
+          w.x = pack_bf16x2(__uint_as_float(a[i + 0]) * is, __uint_as_float(a[i + 1]) * is);
+          w.y = pack_bf16x2(__uint_as_float(a[i + 2]) * is, __uint_as_float(a[i + 3]) * is);
+          w.z = pack_bf16x2(__uint_as_float(a[i + 4]) * is, __uint_as_float(a[i + 5]) * is);
+          w.w = pack_bf16x2(__uint_as_float(a[i + 6]) * is, __uint_as_float(a[i + 7]) * is);
+          const uint32_t off = sw128_offset(r, part * 4 + (i >> 3));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_v + off), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+          w.x = pack_bf16x2(__uint_as_float(b[i + 0]), __uint_as_float(b[i + 1]));
+          w.y = pack_bf16x2(__uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
+          w.z = pack_bf16x2(__uint_as_float(b[i + 4]), __uint_as_float(b[i + 5]));
+          w.w = pack_bf16x2(__uint_as_float(b[i + 6]), __uint_as_float(b[i + 7]));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_k + off), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
         }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);                  // the eight compute warps
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmap_dv),
+                       "r"(smem_u32(sQ) + h * kHalf), "r"(h * 64), "r"(kvh), "r"(k0)
+                       : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmap_dk),
+                       "r"(smem_u32(sQ) + kTile + h * kHalf), "r"(h * 64), "r"(kvh), "r"(k0)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       }
     }
   } else {
@@ -1020,6 +1039,9 @@ static int tree_attn_bwd_impl(const void* q, const void* k, const void* v, const
   if ((rc = make_tmap_bf16_rows(&tdo, dout, sh->n_nodes, sh->n_q_heads, kT, sh->o_row_stride, sh->o_head_stride, kT))) return rc;
   CUtensorMap tdq;
   if ((rc = make_tmap_f32_2d(&tdq, dq_accum, static_cast<int64_t>(sh->n_q_heads) * kT, sh->n_pad, 32, kDqRows))) return rc;
+  CUtensorMap tdk, tdv;     // dK / dV stores of the single-CTA kernel's whole tiles (dk: the k strides, dv: the v strides)
+  if ((rc = make_tmap_bf16_rows(&tdk, dk, sh->n_nodes, sh->n_kv_heads, kT, sh->k_row_stride, sh->k_head_stride, kT))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tdv, dv, sh->n_nodes, sh->n_kv_heads, kT, sh->v_row_stride, sh->v_head_stride, kT))) return rc;
 
   BwdParams p;
   p.aug_lse = reinterpret_cast<const __nv_bfloat16*>(aug_lse);
@@ -1053,7 +1075,7 @@ static int tree_attn_bwd_impl(const void* q, const void* k, const void* v, const
   p.trace = g_bwd_trace;
 
   using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                          const BwdParams);
+                          const CUtensorMap, const CUtensorMap, const BwdParams);
   // tuning knobs: DTA_BWD_POLY = share (of 8) of the exponentials computed on the FMA pipes; DTA_BWD_DQ_TMA = 0
   // selects the per-lane red path for dQ instead of the TMA tensor reduce (work-list schedule only)
   static Kernel kernels[2] = {nullptr, nullptr};          // [whole tiles, work list]
@@ -1080,7 +1102,7 @@ static int tree_attn_bwd_impl(const void* q, const void* k, const void* v, const
       return rc;
   } else {
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
-  kernel<<<(whole_tiles ? n_tiles : wl.work_cap) * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, tdq, p);
+  kernel<<<(whole_tiles ? n_tiles : wl.work_cap) * sh->n_kv_heads, kBwdThreads, BwdSmem::total, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
   }
