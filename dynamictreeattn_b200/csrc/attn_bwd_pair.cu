@@ -221,13 +221,19 @@ __device__ __forceinline__ void pwait_cluster(uint64_t* bar, uint32_t parity) { 
 // time) instead of the KV heads of a pair side by side; compile-time so that the step loop's code is the same
 static constexpr bool kDefaultPairHeadMajor = false;
 static constexpr int kDefaultHandoff = 0;            // bit mask of hand-offs sent as commit signals (see Params::handoff_commit)
-template <int kPolyOf8, bool kHeadMajor>
+// kTmaEpilogue: dV / dK leave through the (dead) Q stages and a TMA store per tensor instead of one 128-byte row per
+// thread straight to global memory (32 rows per store instruction; see attn_bwd.cu's epilogue).  Default since the
+// in-step A/B of profiles/r02/bench_ab10_*.json (one box, alternating): 781.2 / 782.5 ms per step against 784.9 / 785.8;
+// alone the two are equal within noise.  DTA_PAIR_TMA_EPILOGUE=0 selects the row stores.
+static constexpr bool kDefaultPairTmaEpilogue = true;
+template <int kPolyOf8, bool kHeadMajor, bool kTmaEpilogue>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __grid_constant__ CUtensorMap tmap_q128,
                           const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                           const __grid_constant__ CUtensorMap tmap_do64, const __grid_constant__ CUtensorMap tmap_do128,
                           const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_aug_lse,
-                          const __grid_constant__ CUtensorMap tmap_aug_delta, const Params p) {
+                          const __grid_constant__ CUtensorMap tmap_aug_delta, const __grid_constant__ CUtensorMap tmap_dk,
+                          const __grid_constant__ CUtensorMap tmap_dv, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem + Smem::k;
   uint8_t* sV = smem + Smem::v;
@@ -588,15 +594,14 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
     // ---- epilogue: dV, dK -> bf16 ----------------------------------------------------------
     pwait(bar_dkv_full, 0);
     tc_fence_after();
-    __nv_bfloat16* dv_row = p.dv + static_cast<int64_t>(k_idx) * p.v_row_stride + static_cast<int64_t>(kvh) * p.v_head_stride + ch * 64;
-    __nv_bfloat16* dk_row = p.dk + static_cast<int64_t>(k_idx) * p.k_row_stride + static_cast<int64_t>(kvh) * p.k_head_stride + ch * 64;
+    if (kTmaEpilogue) {
+      const uint32_t st_v = smem_u32(sQ) + ch * kHalf, st_k = smem_u32(sQ) + kTile + ch * kHalf;
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
-      uint32_t a[32], b[32];
-      tmem_ld_x32(RdV + lane_addr + ch * 64 + part * 32, a);
-      tmem_ld_x32(RdK + lane_addr + ch * 64 + part * 32, b);
-      tmem_ld_wait();
-      if (k_idx < p.n_nodes) {
+      for (int part = 0; part < 2; ++part) {
+        uint32_t a[32], b[32];
+        tmem_ld_x32(RdV + lane_addr + ch * 64 + part * 32, a);
+        tmem_ld_x32(RdK + lane_addr + ch * 64 + part * 32, b);
+        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 w;
@@ -605,12 +610,55 @@ tree_attn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q64, const __
           w.y = pack_bf16x2(__uint_as_float(a[i + 2]) * is, __uint_as_float(a[i + 3]) * is);
           w.z = pack_bf16x2(__uint_as_float(a[i + 4]) * is, __uint_as_float(a[i + 5]) * is);
           w.w = pack_bf16x2(__uint_as_float(a[i + 6]) * is, __uint_as_float(a[i + 7]) * is);
-          *reinterpret_cast<uint4*>(dv_row + part * 32 + i) = w;
+          const uint32_t off = sw128_offset(r, part * 4 + (i >> 3));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_v + off), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
           w.x = pack_bf16x2(__uint_as_float(b[i + 0]), __uint_as_float(b[i + 1]));
           w.y = pack_bf16x2(__uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
           w.z = pack_bf16x2(__uint_as_float(b[i + 4]), __uint_as_float(b[i + 5]));
           w.w = pack_bf16x2(__uint_as_float(b[i + 6]), __uint_as_float(b[i + 7]));
-          *reinterpret_cast<uint4*>(dk_row + part * 32 + i) = w;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_k + off), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);                  // the eight compute warps of this CTA
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmap_dv),
+                       "r"(smem_u32(sQ) + h * kHalf), "r"(h * 64), "r"(kvh), "r"(k0)
+                       : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmap_dk),
+                       "r"(smem_u32(sQ) + kTile + h * kHalf), "r"(h * 64), "r"(kvh), "r"(k0)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+    } else {
+      __nv_bfloat16* dv_row = p.dv + static_cast<int64_t>(k_idx) * p.v_row_stride + static_cast<int64_t>(kvh) * p.v_head_stride + ch * 64;
+      __nv_bfloat16* dk_row = p.dk + static_cast<int64_t>(k_idx) * p.k_row_stride + static_cast<int64_t>(kvh) * p.k_head_stride + ch * 64;
+  #pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        uint32_t a[32], b[32];
+        tmem_ld_x32(RdV + lane_addr + ch * 64 + part * 32, a);
+        tmem_ld_x32(RdK + lane_addr + ch * 64 + part * 32, b);
+        tmem_ld_wait();
+        if (k_idx < p.n_nodes) {
+  #pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            const float is = p.inv_scale;
+            w.x = pack_bf16x2(__uint_as_float(a[i + 0]) * is, __uint_as_float(a[i + 1]) * is);
+            w.y = pack_bf16x2(__uint_as_float(a[i + 2]) * is, __uint_as_float(a[i + 3]) * is);
+            w.z = pack_bf16x2(__uint_as_float(a[i + 4]) * is, __uint_as_float(a[i + 5]) * is);
+            w.w = pack_bf16x2(__uint_as_float(a[i + 6]) * is, __uint_as_float(a[i + 7]) * is);
+            *reinterpret_cast<uint4*>(dv_row + part * 32 + i) = w;
+            w.x = pack_bf16x2(__uint_as_float(b[i + 0]), __uint_as_float(b[i + 1]));
+            w.y = pack_bf16x2(__uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
+            w.z = pack_bf16x2(__uint_as_float(b[i + 4]), __uint_as_float(b[i + 5]));
+            w.w = pack_bf16x2(__uint_as_float(b[i + 6]), __uint_as_float(b[i + 7]));
+            *reinterpret_cast<uint4*>(dk_row + part * 32 + i) = w;
+          }
         }
       }
     }
@@ -773,11 +821,17 @@ int launch(const void* q, const void* k, const void* v, const void* dout, const 
   p.handoff_commit = !ho ? kDefaultHandoff : strcmp(ho, "commit") == 0 ? 7 : strcmp(ho, "commit_p") == 0 ? 1 : strcmp(ho, "commit_ds") == 0 ? 2
                      : strcmp(ho, "commit_r1") == 0 ? 4 : strcmp(ho, "commit_p_ds") == 0 ? 3 : strcmp(ho, "arrive") == 0 ? 0 : kDefaultHandoff;
 
+  CUtensorMap tdk, tdv;     // kTmaEpilogue stores (dk: the k strides, dv: the v strides)
+  if ((rc = make_tmap_bf16_rows(&tdk, dk, sh->n_nodes, sh->n_kv_heads, kT, sh->k_row_stride, sh->k_head_stride, kT))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tdv, dv, sh->n_nodes, sh->n_kv_heads, kT, sh->v_row_stride, sh->v_head_stride, kT))) return rc;
   using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                          const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
-  static const Kernel kernels[6] = {tree_attn_bwd_pair_kernel<0, false>, tree_attn_bwd_pair_kernel<2, false>,
-                                    tree_attn_bwd_pair_kernel<4, false>, tree_attn_bwd_pair_kernel<0, true>,
-                                    tree_attn_bwd_pair_kernel<2, true>, tree_attn_bwd_pair_kernel<4, true>};
+                          const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                          const CUtensorMap, const Params);
+  // [TMA epilogue][poly 0 / 2 / 4, then head-major with poly 0]: the rejected variants stay reachable for A/B runs
+  static const Kernel kernels[8] = {tree_attn_bwd_pair_kernel<0, false, false>, tree_attn_bwd_pair_kernel<2, false, false>,
+                                    tree_attn_bwd_pair_kernel<4, false, false>, tree_attn_bwd_pair_kernel<0, true, false>,
+                                    tree_attn_bwd_pair_kernel<0, false, true>,  tree_attn_bwd_pair_kernel<2, false, true>,
+                                    tree_attn_bwd_pair_kernel<4, false, true>,  tree_attn_bwd_pair_kernel<0, true, true>};
   static bool configured = false;
   if (!configured) {
     for (Kernel kf : kernels) DTA_CHECK_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
@@ -787,9 +841,11 @@ int launch(const void* q, const void* k, const void* v, const void* dout, const 
   const int poly = pe ? atoi(pe) : 0;
   const char* hm = getenv("DTA_BWD_HEAD_MAJOR");           // A/B knob (round 2, in-step): see kDefaultPairHeadMajor
   const bool head_major = hm ? atoi(hm) != 0 : kDefaultPairHeadMajor;
-  const Kernel kernel = kernels[(head_major ? 3 : 0) + (poly <= 0 ? 0 : poly <= 2 ? 1 : 2)];
+  const char* te = getenv("DTA_PAIR_TMA_EPILOGUE");        // A/B knob
+  const bool tma_epilogue = te ? atoi(te) != 0 : kDefaultPairTmaEpilogue;
+  const Kernel kernel = kernels[(tma_epilogue ? 4 : 0) + (head_major ? 3 : (poly <= 0 ? 0 : poly <= 2 ? 1 : 2))];
   if (ev_start) DTA_CHECK_CUDA(cudaEventRecord(ev_start, stream));
-  kernel<<<2 * n_pairs * sh->n_kv_heads, kThreads, Smem::total, stream>>>(tq64, tq128, tk, tv, tdo64, tdo128, tdq, taug_l, taug_d, p);
+  kernel<<<2 * n_pairs * sh->n_kv_heads, kThreads, Smem::total, stream>>>(tq64, tq128, tk, tv, tdo64, tdo128, tdq, taug_l, taug_d, tdk, tdv, p);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (ev_stop) DTA_CHECK_CUDA(cudaEventRecord(ev_stop, stream));
   return DTA_OK;
