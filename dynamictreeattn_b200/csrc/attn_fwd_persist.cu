@@ -44,6 +44,11 @@ namespace fwd_persist {
 static constexpr int kEndSlots = 4;
 static constexpr int kEndBytes = kBN * 4;
 static constexpr int kItemSlots = 4;
+// Two softmax threads per row (Roles / kSplit below).  MEASURED SLOWER and therefore off: tau2 1018 against 1128 TFLOP/s
+// alone, 967 against 1070 inside the step (profiles/r02/bench_ab11_*.json, attn_bushy_fwd_split{0,1}.jsonl).  The two
+// softmax warps a scheduler already hosts (heads A and B) keep its issue slots and the MUFU pipe busy between them;
+// four half-length warps do the same work plus the exchange, at 104 registers instead of 224.  DTA_FWD_SPLIT=1: A/B knob.
+static constexpr bool kDefaultSplit = false;
 static constexpr int kSlotLive = kPersistMaxTiles;
 
 struct Smem {
@@ -54,7 +59,8 @@ struct Smem {
   static constexpr int live = ends + kEndSlots * kEndBytes;    // kItemSlots x uint16[kSlotLive]: (key tile << 1) | boundary
   static constexpr int qorder = live + kItemSlots * kSlotLive * 2;   // uint16[kSlotLive]: q_order, read once
   static constexpr int meta = qorder + kSlotLive * 2;          // kItemSlots x {query tile, head pair, n_live (-1: no more work), -}
-  static constexpr int bars = meta + kItemSlots * 16;
+  static constexpr int xch = meta + kItemSlots * 16;           // kSplit: row maxima (two step parities) and row sums, [t][h][row] floats
+  static constexpr int bars = xch + 3 * 2048;
   static constexpr int n_bars = 2 + 4 * kStages + 8 + 2 * kItemSlots;
   static constexpr int misc = bars + n_bars * 8;               // tmem addr
   static constexpr int total = misc + 16;
@@ -79,6 +85,14 @@ __device__ __forceinline__ int lds_u16(uint32_t addr) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
   return r;
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
 }
@@ -96,8 +110,24 @@ static constexpr int kTraceItems = 24, kTraceEvents = 24;
     if (kTrace && blockIdx.x == 0 && ic < kTraceItems) trace[ic * kTraceEvents + (ev)] = clock64(); \
   } while (0)
 
-template <int kPolyOf8, bool kTrace>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+// kSplit: TWO softmax threads per query row (16 softmax warps; warps w and w + 8 share 32 rows and take the key halves
+// [0, 64) / [64, 128) of every tile).  One thread per row makes the softmax of a tile an ~1,860-cycle dependency chain
+// of ONE warp per scheduler, and the per-head chain S -> softmax -> PV -> S is what leaves the tensor pipe ~60 % busy
+// (attn_fwd.cu's header); halving the chain needs only the row maximum exchanged per step (4 bytes per thread through
+// shared memory + a 64-thread named barrier) and the row sums once per item.  P halves land in disjoint TMEM columns;
+// the half that overwrites the other's S columns does so behind the barrier, i.e. after the other half has loaded them.
+template <bool kSplit>
+struct Roles {
+  static constexpr int softmax_warps = kSplit ? 16 : 8;
+  static constexpr int store_warp0 = softmax_warps;        // two O store warps
+  static constexpr int producer = softmax_warps + 2;
+  static constexpr int mma = softmax_warps + 3;            // highest warp slot: highest arbiter priority
+  static constexpr int threads = (softmax_warps + 4) * 32;
+  static constexpr int row_threads = kSplit ? 256 : 128;   // arrivals per tile on the P / O-staged barriers
+};
+
+template <int kPolyOf8, bool kTrace, bool kSplit>
+__global__ void __launch_bounds__(Roles<kSplit>::threads, 1)
 tree_attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                              const FwdParams p, int* counters, int n_items, long long* trace) {
@@ -126,6 +156,8 @@ tree_attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::misc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  using R = Roles<kSplit>;
+  constexpr int kProducerWarp = R::producer, kMmaWarp = R::mma;      // shadow attn_fwd.cuh's (the 12-warp layout)
 
   // ---- setup ---------------------------------------------------------------------------
   if (warp == kProducerWarp) {
@@ -147,13 +179,13 @@ tree_attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
       }
       for (int t = 0; t < 2; ++t) {
         mbar_init(bar_s_full + t, 1);
-        mbar_init(bar_p_full + t, 128);
+        mbar_init(bar_p_full + t, R::row_threads);
         mbar_init(bar_o_final + t, 1);
-        mbar_init(bar_o_staged + t, 128);
+        mbar_init(bar_o_staged + t, R::row_threads);
       }
       for (int s = 0; s < kItemSlots; ++s) {
         mbar_init(bar_item_full + s, 1);
-        mbar_init(bar_item_empty + s, 10);                 // 8 softmax warps + 2 store warps
+        mbar_init(bar_item_empty + s, R::softmax_warps + 2);   // softmax warps + 2 store warps
       }
       fence_mbar_init();
     }
@@ -348,10 +380,10 @@ tree_attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
       __syncwarp();
       if (lane == 0) DTA_FTRACE(8);
     }
-  } else if (warp >= 8) {
-    // ================================ O store warps (8: head A, 9: head B) ================
+  } else if (warp >= R::store_warp0) {
+    // ================================ O store warps (head A, head B) ======================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    const int t = warp - 8;
+    const int t = warp - R::store_warp0;
     uint32_t g = 0, done = 0;
     for (int ic = 0;; ++ic) {
       const int buf = ic & (kItemSlots - 1);
@@ -381,6 +413,173 @@ tree_attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
+    if constexpr (kSplit) {
+    // ================================ softmax + epilogue, two threads per row ============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");   // 640 threads start at 96; the four role warps release 4 x 32 x 40 = 5,120 registers, 16 x 32 x 8 = 4,096 are taken here
+    const int t = (warp >> 2) & 1;                 // tile A / B
+    const int h = warp >> 3;                       // key half of every tile: columns [64h, 64h + 64)
+    const int row = ((warp & 3) << 5) | lane;      // TMEM lane == query row inside the tile
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) << 5) << 16;
+    const uint32_t tS = tmem + lane_addr + t * 128;
+    const uint32_t tO = tmem + lane_addr + 256 + t * 128 + h * 64;
+    const uint32_t xch = smem_u32(smem + Smem::xch);
+    const uint32_t x_mine = xch + ((t * 2 + h) * 128 + row) * 4, x_other = xch + ((t * 2 + (h ^ 1)) * 128 + row) * 4;
+    const uint32_t pair_bar = 1 + t * 4 + (warp & 3);   // named barrier of the two warps that share these 32 rows
+    uint32_t g = 0;                                // ring position of the item's first key tile
+    uint32_t steps = 0, done = 0;                  // S tiles / items this warp has worked on (barrier phases)
+    for (int ic = 0;; ++ic) {
+      const int buf = ic & (kItemSlots - 1);
+      mbar_wait_timed(bar_item_full + buf, (ic / kItemSlots) & 1);
+      const uint32_t meta = smem_u32(smem + Smem::meta) + buf * 16;
+      const int n_live = lds_s32(meta + 8);
+      if (n_live < 0) break;
+      const int qtile = lds_s32(meta);
+      const int pair = lds_s32(meta + 4);
+      const int kvh = pair / p.pairs_per_kv;
+      const int head = kvh * p.group + 2 * (pair % p.pairs_per_kv) + t;
+      const bool valid = t == 0 || (2 * (pair % p.pairs_per_kv) + 1) < p.group;
+      const uint32_t live = smem_u32(sLive) + buf * (kSlotLive * 2);
+      const bool tracer = kTrace && (warp & 3) == 0 && h == 0 && lane == 0;
+      if (tracer) DTA_FTRACE(9 + 5 * t);
+      if (valid) {
+        const int q0 = qtile * kBM;
+        const int q = q0 + row;
+        float m2 = -INFINITY;   // running max of the WHOLE row (both halves keep the same value), log2 domain
+        float l = 0.f;          // running sum of 2^(z - m2) over this thread's key half
+
+        for (int it = 0; it < n_live; ++it, ++steps) {
+          const int entry = lds_u16(live + it * 2);
+          const int k0 = (entry >> 2) * kBN + h * 64;          // first key of this thread's half
+          mbar_wait_timed(bar_s_full + t, steps & 1);
+          if (tracer && it == 0) DTA_FTRACE(10 + 5 * t);
+          tc_fence_after();
+          float s[64];
+          tmem_ld_x32(tS + h * 64, reinterpret_cast<uint32_t*>(s));
+          tmem_ld_x32(tS + h * 64 + 32, reinterpret_cast<uint32_t*>(s) + 32);
+          tmem_ld_wait();
+
+          if (entry & 2) {  // diagonal tile inside a branch: causal
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              if (h * 64 + i > row) s[i] = -INFINITY;
+          } else if (entry & 1) {  // boundary tile: per-element ancestor test against the tile's subtree ends
+            const uint32_t ends = smem_u32(sEnds) + ((g + it) & (kEndSlots - 1)) * kEndBytes + h * 256;
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+              const int4 e = lds_v4(ends + c4 * 16);
+              const int kb = k0 + c4 * 4;
+              if (!(kb + 0 <= q && q < e.x)) s[c4 * 4 + 0] = -INFINITY;
+              if (!(kb + 1 <= q && q < e.y)) s[c4 * 4 + 1] = -INFINITY;
+              if (!(kb + 2 <= q && q < e.z)) s[c4 * 4 + 2] = -INFINITY;
+              if (!(kb + 3 <= q && q < e.w)) s[c4 * 4 + 3] = -INFINITY;
+            }
+          }
+          float mx = s[0];
+#pragma unroll
+          for (int c = 1; c < 64; ++c) mx = fmaxf(mx, s[c]);
+          // the row maximum over both halves.  The barrier also orders this half's S loads before the other half's
+          // P stores into the same TMEM columns.
+          const uint32_t par = (steps & 1) * 2048;
+          sts_f32(x_mine + par, mx);
+          named_bar_sync(pair_bar, 64);
+          mx = fmaxf(mx, lds_f32(x_other + par));
+          mx *= p.scale_log2;
+
+          float alpha = 1.f;
+          if (mx > m2 + kRescaleThreshold) {
+            alpha = fast_exp2(m2 - mx);  // m2 == -inf -> 0
+            m2 = mx;
+          }
+          if (it > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {   // same vote in both warps of the pair
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {          // rare path (lazy rescale): 16 columns at a time, rolled
+              uint32_t o[16];
+              tmem_ld_x16(tO + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x16(tO + c * 16, o);
+            }
+            tmem_st_wait();
+          }
+          l *= alpha;
+          const float mref = (m2 == -INFINITY) ? 0.f : m2;
+          const uint64_t scale2 = f2_bcast(p.scale_log2), nmref2 = f2_bcast(-mref);
+          uint64_t lsum_a = f2_bcast(0.f), lsum_b = f2_bcast(0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint64_t x2 = f2_fma(f2_pack(s[c * 16 + 2 * i], s[c * 16 + 2 * i + 1]), scale2, nmref2);
+              uint64_t p2;
+              if (exp2_pair_on_fma<kPolyOf8>(i)) {
+                p2 = poly_exp2_x2(x2);
+              } else {
+                float x0, x1;
+                f2_unpack(x2, x0, x1);
+                p2 = f2_pack(fast_exp2(x0), fast_exp2(x1));
+              }
+              if (i & 1) lsum_b = f2_add(lsum_b, p2); else lsum_a = f2_add(lsum_a, p2);
+              float p0, p1;
+              f2_unpack(p2, p0, p1);
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+            tmem_st_x8(tS + h * 32 + c * 8, pk);
+          }
+          {
+            float la, lb;
+            f2_unpack(f2_add(lsum_a, lsum_b), la, lb);
+            l += la + lb;
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_p_full + t);
+          if (tracer && it + 1 == n_live) DTA_FTRACE(11 + 5 * t);
+        }
+
+        // ---- epilogue: O / l -> bf16, LSE -----------------------------------------------
+        mbar_wait_timed(bar_o_final + t, done & 1);
+        if (tracer) DTA_FTRACE(12 + 5 * t);
+        ++done;
+        tc_fence_after();
+        sts_f32(x_mine + 4096, l);
+        named_bar_sync(pair_bar, 64);
+        const float l_other = lds_f32(x_other + 4096);
+        const float lt = h == 0 ? l + l_other : l_other + l;        // the same sum, in the same order, in both threads
+        const float inv_l = lt > 0.f ? 1.f / lt : 0.f;
+        if (h == 0 && q < p.n_pad) {
+          float lse = 0.f;
+          if (q < p.n_nodes) lse = m2 + log2f(lt);     // base-2 log-sum-exp of the scaled scores
+          p.lse[static_cast<int64_t>(head) * p.n_pad + q] = lse;
+        }
+        // this thread's 64 O columns into its half of the staging tile
+        const uint32_t stage = smem_u32(t == 0 ? sV : sK) + ((g + n_live - 1) % kStages) * kTileBytes + h * kHalfBytes;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[i + 0]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            sts_v4(stage + sw128_offset(row, c * 4 + (i >> 3)), w);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_o_staged + t);
+        if (tracer) DTA_FTRACE(13 + 5 * t);
+      }
+      g += static_cast<uint32_t>(n_live);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_item_empty + buf);
+    }
+    } else {
     // ================================ softmax + epilogue =================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int t = warp >> 2;                       // tile A / B
@@ -536,6 +735,7 @@ tree_attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_item_empty + buf);
     }
+    }
   }
 
   // ---- teardown --------------------------------------------------------------------------
@@ -579,15 +779,24 @@ int launch_tree_attn_fwd_persist(const CUtensorMap& tq, const CUtensorMap& tk, c
   const int smem_bytes = Smem::total + 1024;
   static Kernel kernel = nullptr;
   static long long* trace = nullptr;
+  static int threads = 0;
   if (!kernel) {
     // DTA_FWD_PERSIST_TRACE = device address (decimal) of kTraceItems x kTraceEvents int64: tools/fwd_persist_trace.py
     const char* te = getenv("DTA_FWD_PERSIST_TRACE");
     if (te && *te) trace = reinterpret_cast<long long*>(strtoull(te, nullptr, 10));
-    Kernel k = trace ? tree_attn_fwd_persist_kernel<kDefaultFwdPoly, true>
-             : poly_of_8 <= 1 ? tree_attn_fwd_persist_kernel<0, false> : poly_of_8 <= 3 ? tree_attn_fwd_persist_kernel<2, false>
-             : poly_of_8 <= 5 ? tree_attn_fwd_persist_kernel<4, false> : poly_of_8 <= 7 ? tree_attn_fwd_persist_kernel<6, false>
-                              : tree_attn_fwd_persist_kernel<8, false>;
+    const char* se = getenv("DTA_FWD_SPLIT");                // A/B knob: two softmax threads per row (kSplit)
+    const bool split = se ? atoi(se) != 0 : kDefaultSplit;
+    Kernel k;
+    if (split)
+      k = trace ? tree_attn_fwd_persist_kernel<kDefaultFwdPoly, true, true>
+        : poly_of_8 <= 1 ? tree_attn_fwd_persist_kernel<0, false, true> : poly_of_8 <= 3 ? tree_attn_fwd_persist_kernel<2, false, true>
+        : poly_of_8 <= 5 ? tree_attn_fwd_persist_kernel<4, false, true> : tree_attn_fwd_persist_kernel<6, false, true>;
+    else
+      k = trace ? tree_attn_fwd_persist_kernel<kDefaultFwdPoly, true, false>
+        : poly_of_8 <= 1 ? tree_attn_fwd_persist_kernel<0, false, false> : poly_of_8 <= 3 ? tree_attn_fwd_persist_kernel<2, false, false>
+        : poly_of_8 <= 5 ? tree_attn_fwd_persist_kernel<4, false, false> : tree_attn_fwd_persist_kernel<6, false, false>;
     DTA_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    threads = split ? Roles<true>::threads : Roles<false>::threads;
     kernel = k;
   }
   int* counters = nullptr;
@@ -598,7 +807,7 @@ int launch_tree_attn_fwd_persist(const CUtensorMap& tq, const CUtensorMap& tk, c
   const int n_items = p.n_tiles * p.n_kv_heads * p.pairs_per_kv;
   const int grid = n_items < sm_count() ? n_items : sm_count();
   if (hook.start) DTA_CHECK_CUDA(cudaEventRecord(hook.start, stream));
-  kernel<<<grid, kFwdThreads, smem_bytes, stream>>>(tq, tk, tv, to, p, counters, n_items, trace);
+  kernel<<<grid, threads, smem_bytes, stream>>>(tq, tk, tv, to, p, counters, n_items, trace);
   DTA_CHECK_CUDA(cudaGetLastError());
   if (hook.stop) DTA_CHECK_CUDA(cudaEventRecord(hook.stop, stream));
   return DTA_OK;
