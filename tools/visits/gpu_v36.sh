@@ -10,7 +10,7 @@ echo "bushy exit $?"; python - <<'PY'
 import json
 for l in open('gpurun_out/attn_bushy_persist.jsonl'):
     d = json.loads(l)
-    print(d['case'], 'auto', d['fwd_tflops'], 'one-item', d['fwd_one_item_per_cta_tflops'], 'persistent', d['fwd_persistent_tflops'], 'bwd', d['bwd_tflops'], 'auto_is_persistent', d['fwd_auto_is_persistent'])
+    print(d['case'], 'auto', d['fwd_tflops'], 'one-item', d['fwd_one_item_per_cta_tflops'], 'persistent', d['fwd_persistent_tflops'], 'bwd', d['bwd_tflops'])
 PY
 F="--no-cpu-baseline --no-dense-baseline --no-gpu-reference --no-strong --no-calibrate --no-vocab-parallel"
 i=0
