@@ -37,6 +37,7 @@
 #include "attn_fwd.cuh"
 #include <atomic>
 #include <cstdlib>
+#include <mutex>
 
 namespace dta {
 namespace fwd_persist {
@@ -756,9 +757,11 @@ static constexpr int kMaxDevices = 64;
 static int counter_slot(int** out) {
   static int* pool[kMaxDevices] = {};
   static std::atomic<unsigned> turn{0};
+  static std::mutex mu;                  // first call per device from two host threads at once
   int dev = 0;
   DTA_CHECK_CUDA(cudaGetDevice(&dev));
   DTA_REQUIRE(dev >= 0 && dev < kMaxDevices, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
   if (!pool[dev]) {
     int* ptr = nullptr;
     DTA_CHECK_CUDA(cudaMalloc(&ptr, kSlots * kSlotInts * sizeof(int)));
