@@ -738,6 +738,25 @@ def test_bwd_cta_pair_commit_handoff_variant(name, monkeypatch):
         assert torch.isfinite(b.float()).all() and _rel(b, a) < 1e-4
 
 
+@pytest.mark.parametrize("name,heads", [("chain_300", (4, 2)), ("deep_forks", (2, 1)), ("tau2_mini", (16, 8))])
+def test_bwd_cta_pair_row_store_epilogue_variant(name, heads, monkeypatch):
+    """DTA_PAIR_TMA_EPILOGUE=0 (dK / dV as one row per thread straight to global memory, the form before the TMA-store
+    epilogue became the default) writes the same bytes: dk and dv are BIT-equal, dq differs only by the order of the
+    fp32 reduce-adds."""
+    from dynamictreeattn_b200.attention import tree_attention
+    trie, lay = _layout(name)
+    q, k, v, do = _qkv(lay.n_nodes, *heads)
+    monkeypatch.setenv("DTA_BWD_PAIR", "1")
+    grads = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DTA_PAIR_TMA_EPILOGUE", mode)
+        qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+        tree_attention(qq, kk, vv, lay, 128 ** -0.5).backward(do)
+        grads[mode] = (qq.grad, kk.grad, vv.grad)
+    assert torch.equal(grads["0"][1], grads["1"][1]) and torch.equal(grads["0"][2], grads["1"][2])
+    assert _rel(grads["0"][0], grads["1"][0]) < 1e-4
+
+
 def test_constant_values_property_full_size():
     """Size-independent property at BASELINE size (tau2-16k shape, 67k trie tokens, Hq 16 / Hkv 8):
     with V == 1 every softmax row must sum to 1 -> out == 1 exactly up to bf16; and dV == sum over
